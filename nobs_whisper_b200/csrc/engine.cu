@@ -1,0 +1,784 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+#include "gemm_sm100.cuh"
+
+namespace nobs {
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            err_ = std::string(#expr) + " failed: " + cudaGetErrorString(e_);                  \
+            return false;                                                                      \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoi(s);
+}
+
+// GEMM dispatch by storage type.  fp32 parity mode runs on CUDA cores; bf16 runs the
+// tcgen05/TMA kernel (gemm_sm100.cu).
+inline bool gemm(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
+    launch_gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    return true;
+}
+inline bool gemm(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
+    return launch_gemm_bf16_sm100(A, lda, W, ldw, C, ldc, /*c_is_f32=*/false, M, N, K, e, s);
+}
+inline bool gemm(const bf16* A, int lda, const bf16* W, int ldw, float* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
+    return launch_gemm_bf16_sm100(A, lda, W, ldw, C, ldc, /*c_is_f32=*/true, M, N, K, e, s);
+}
+inline bool enc_attention(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s) {
+    launch_enc_attention_f32(qkv, out, n_win, n_head, d, s);
+    return true;
+}
+inline bool enc_attention(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s) {
+    return launch_enc_attention_bf16_sm100(qkv, out, n_win, n_head, d, s);
+}
+
+template <typename T>
+struct Layer {
+    float *ln1_g, *ln1_b;
+    T* wqkv; float* bqkv;
+    T* wo; float* bo;
+    float *lnc_g, *lnc_b;  // decoder only
+    T* wcq; float* bcq;
+    T* wco; float* bco;
+    float *ln2_g, *ln2_b;
+    T* w1; float* b1;
+    T* w2; float* b2;
+};
+
+template <typename T>
+class EngineT final : public Engine {
+public:
+    EngineT(const HostModel& hm, int device, Precision prec) : hp_(hm.hp) {
+        device_ = device;
+        prec_ = prec;
+    }
+    ~EngineT() override {
+        cudaSetDevice(device_);
+        if (stream_) cudaStreamSynchronize(stream_);
+        for (void* p : owned_) cudaFree(p);
+        for (auto& m : mel_cache_) { cudaFree(m.raw); cudaFree(m.max_key); }
+        if (pin_) cudaFreeHost(pin_);
+        if (cross_pool_) cudaFree(cross_pool_);
+        if (self_pool_) cudaFree(self_pool_);
+        if (encout_pool_) cudaFree(encout_pool_);
+        if (pcm_dev_) cudaFree(pcm_dev_);
+        for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+
+    bool init(const HostModel& hm) {
+        int n_dev = 0;
+        CUDA_OK(cudaGetDeviceCount(&n_dev));
+        if (device_ < 0 || device_ >= n_dev) { err_ = "invalid CUDA device " + std::to_string(device_); return false; }
+        CUDA_OK(cudaSetDevice(device_));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device_));
+        if (prop.major != 10) { err_ = std::string("device '") + prop.name + "' is not sm_100 (this library has no other code path)"; return false; }
+        CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        for (auto& e : ev_) CUDA_OK(cudaEventCreate(&e));
+        d_ = hp_.n_audio_state;
+        const Vocab& v = hm.vocab;
+        vocab_ids = VocabIds{hp_.n_vocab, v.token_eot, v.token_sot, v.token_translate, v.token_transcribe, v.token_solm, v.token_prev,
+                             v.token_nosp, v.token_not, v.token_beg, v.token_blank, kNumLangs};
+        if (!upload_weights(hm)) return false;
+        if (!alloc_workspace()) return false;
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+
+    // ------------------------------------------------------------------ slots
+    int acquire_audio_slot() override {
+        if (audio_free_.empty() && !grow_audio(std::max(1, audio_cap_ * 2))) return -1;
+        int s = audio_free_.back();
+        audio_free_.pop_back();
+        return s;
+    }
+    void release_audio_slot(int s) override { if (s >= 0) audio_free_.push_back(s); }
+    int acquire_kv_slot() override {
+        if (kv_free_.empty() && !grow_kv(std::max(1, kv_cap_ * 2))) return -1;
+        int s = kv_free_.back();
+        kv_free_.pop_back();
+        return s;
+    }
+    void release_kv_slot(int s) override { if (s >= 0) kv_free_.push_back(s); }
+    bool reserve_slots(int n_audio_free, int n_kv_free) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if ((int)audio_free_.size() < n_audio_free && !grow_audio(audio_cap_ + n_audio_free - (int)audio_free_.size())) return false;
+        if ((int)kv_free_.size() < n_kv_free && !grow_kv(kv_cap_ + n_kv_free - (int)kv_free_.size())) return false;
+        std::sort(audio_free_.begin(), audio_free_.end(), std::greater<int>());  // pop ascending: consecutive slots per batch
+        std::sort(kv_free_.begin(), kv_free_.end(), std::greater<int>());
+        return true;
+    }
+
+    void free_mel(DeviceMel& m) override {
+        if (m.raw) mel_cache_.push_back(m);
+        m = DeviceMel();
+    }
+
+    // ------------------------------------------------------------------ K1
+    bool compute_mel(const std::vector<MelRequest>& reqs) override {
+        CUDA_OK(cudaSetDevice(device_));
+        const int n = (int)reqs.size();
+        if (n == 0) return true;
+        size_t total = 0;
+        std::vector<size_t> off(n);
+        for (int i = 0; i < n; ++i) { off[i] = total; total += align_up((size_t)std::max(reqs[i].n_samples, 0), 4); }
+        if (total > pcm_cap_) {
+            if (pcm_dev_) CUDA_OK(cudaFree(pcm_dev_));
+            pcm_dev_ = nullptr;
+            pcm_cap_ = align_up(total + total / 4, 1024);
+            CUDA_OK(cudaMalloc(&pcm_dev_, pcm_cap_ * sizeof(float)));
+        }
+        if (!ensure_pin(sizeof(MelJob) * n)) return false;
+        MelJob* jobs = reinterpret_cast<MelJob*>(pin_);
+        int max_frames = 0;
+        CUDA_OK(cudaEventRecord(ev_[0], stream_));
+        for (int i = 0; i < n; ++i) {
+            const MelRequest& r = reqs[i];
+            DeviceMel& m = *r.mel;
+            const int ns = r.n_samples;
+            m.n_mel = hp_.n_mels;
+            m.n_len = (ns + 480000) / kHop;
+            m.n_len_org = 1 + (ns + 200 - kNFft) / kHop;
+            m.n_frames = std::min(m.n_len, (ns + 200 + kHop - 1) / kHop);
+            const size_t need = (size_t)std::max(m.n_frames, 1) * m.n_mel;
+            if (!m.raw || m.raw_cap < need) {
+                if (m.raw) mel_cache_.push_back(m);
+                m.raw = nullptr;
+                if (!take_cached_mel(m, need)) {
+                    m.raw_cap = align_up(need, 4096);
+                    CUDA_OK(cudaMalloc(&m.raw, m.raw_cap * sizeof(float)));
+                    CUDA_OK(cudaMalloc(&m.max_key, sizeof(int)));
+                }
+            }
+            CUDA_OK(cudaMemcpyAsync(m.max_key, &init_key_, sizeof(int), cudaMemcpyHostToDevice, stream_));
+            if (ns > 0) CUDA_OK(cudaMemcpyAsync(pcm_dev_ + off[i], r.pcm, (size_t)ns * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            jobs[i] = MelJob{pcm_dev_ + off[i], ns, m.n_frames, m.raw, m.max_key};
+            max_frames = std::max(max_frames, m.n_frames);
+        }
+        if (!ensure_dev_scratch(sizeof(MelJob) * n)) return false;
+        CUDA_OK(cudaMemcpyAsync(dev_scratch_, jobs, sizeof(MelJob) * n, cudaMemcpyHostToDevice, stream_));
+        launch_mel_stft(mel_tables_, reinterpret_cast<const MelJob*>(dev_scratch_), n, max_frames, stream_);
+        CUDA_OK(cudaEventRecord(ev_[1], stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));  // the pinned job table and the caller's PCM are borrowed
+        CUDA_OK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        stats.ms_mel += ms;
+        return true;
+    }
+
+    // ------------------------------------------------------------------ K2-K4
+    bool encode(const std::vector<EncodeRequest>& reqs) override {
+        CUDA_OK(cudaSetDevice(device_));
+        CUDA_OK(cudaEventRecord(ev_[0], stream_));
+        for (size_t b0 = 0; b0 < reqs.size(); b0 += enc_batch_) {
+            const int nb = (int)std::min<size_t>(enc_batch_, reqs.size() - b0);
+            if (!encode_batch(&reqs[b0], nb)) return false;
+        }
+        CUDA_OK(cudaEventRecord(ev_[1], stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        stats.ms_encode += ms;
+        return true;
+    }
+
+    bool encode_batch(const EncodeRequest* reqs, int nb) {
+        const int d = d_, nm = hp_.n_mels, M = nb * kWinRows;
+        // window descriptors
+        if (!ensure_pin(sizeof(PackJob) * nb)) return false;
+        CUDA_OK(cudaStreamSynchronize(stream_));  // pinned staging is reused across batches
+        PackJob* pj = reinterpret_cast<PackJob*>(pin_);
+        for (int w = 0; w < nb; ++w) {
+            const DeviceMel& m = *reqs[w].mel;
+            if (!m.raw || reqs[w].audio_slot < 0 || reqs[w].audio_slot >= audio_cap_) { err_ = "encode: bad request"; return false; }
+            pj[w] = PackJob{m.raw, m.max_key, m.n_frames, m.n_len, reqs[w].seek};
+        }
+        if (!ensure_dev_scratch(sizeof(PackJob) * nb)) return false;
+        CUDA_OK(cudaMemcpyAsync(dev_scratch_, pj, sizeof(PackJob) * nb, cudaMemcpyHostToDevice, stream_));
+        if (!rezero_conv_pads(nb)) return false;
+        launch_pack_mel<T>(reinterpret_cast<const PackJob*>(dev_scratch_), nb, nm, e_mel_, stream_);
+        // conv1: rows (w, t) read the 3 neighbouring mel frames in place (row stride n_mels, K = 3*n_mels)
+        {
+            Epilogue e;
+            e.bias = conv1_b_; e.act = 1; e.win_rows = kWinRowsIn; e.valid_rows = 3000;
+            if (!gemm(e_mel_, nm, conv1_w_, 3 * nm, e_h1_ + d, d, nb * kWinRowsIn, d, 3 * nm, e, stream_)) return gemm_fail();
+        }
+        // conv2 (stride 2): row (w, t') reads h1 rows 2t'-1..2t'+1 in place (row stride 2d, K = 3d); + positional embedding
+        {
+            Epilogue e;
+            e.bias = conv2_b_; e.act = 1; e.res = enc_pos_; e.res_ld = d; e.res_mod = kWinRows;
+            if (!gemm(e_h1_, 2 * d, conv2_w_, 3 * d, e_x_, d, M, d, 3 * d, e, stream_)) return gemm_fail();
+        }
+        for (int l = 0; l < hp_.n_audio_layer; ++l) {
+            const Layer<T>& L = enc_[l];
+            launch_layernorm<T>(e_x_, d, L.ln1_g, L.ln1_b, e_y_, d, M, d, stream_);
+            { Epilogue e; e.bias = L.bqkv; if (!gemm(e_y_, d, L.wqkv, d, e_qkv_, 3 * d, M, 3 * d, d, e, stream_)) return gemm_fail(); }
+            if (!enc_attention(e_qkv_, e_att_, nb, hp_.n_audio_head, d, stream_)) return gemm_fail();
+            { Epilogue e; e.bias = L.bo; e.res = e_x_; e.res_ld = d; if (!gemm(e_att_, d, L.wo, d, e_x_, d, M, d, d, e, stream_)) return gemm_fail(); }
+            launch_layernorm<T>(e_x_, d, L.ln2_g, L.ln2_b, e_y_, d, M, d, stream_);
+            { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(e_y_, d, L.w1, d, e_h_, 4 * d, M, 4 * d, d, e, stream_)) return gemm_fail(); }
+            { Epilogue e; e.bias = L.b2; e.res = e_x_; e.res_ld = d; if (!gemm(e_h_, 4 * d, L.w2, 4 * d, e_x_, d, M, d, 4 * d, e, stream_)) return gemm_fail(); }
+        }
+        launch_layernorm<T>(e_x_, d, enc_lnp_g_, enc_lnp_b_, e_y_, d, M, d, stream_);
+        // keep the encoder output per audio slot, then project every decoder layer's cross K/V
+        // with one GEMM per run of consecutive slots: out rows land directly in the cross-KV pool.
+        const int ldx = 2 * hp_.n_text_layer * d;
+        int w = 0;
+        while (w < nb) {
+            int run = 1;
+            while (w + run < nb && reqs[w + run].audio_slot == reqs[w].audio_slot + run) ++run;
+            const int s0 = reqs[w].audio_slot;
+            CUDA_OK(cudaMemcpyAsync(encout_pool_ + (size_t)s0 * kWinRows * d, e_y_ + (size_t)w * kWinRows * d,
+                                    (size_t)run * kWinRows * d * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+            Epilogue e;
+            e.bias = cross_b_;
+            if (!gemm(e_y_ + (size_t)w * kWinRows * d, d, cross_w_, d, cross_pool_ + (size_t)s0 * kWinRows * ldx, ldx, run * kWinRows, ldx, d, e, stream_))
+                return gemm_fail();
+            w += run;
+        }
+        return true;
+    }
+
+    // ------------------------------------------------------------------ K5 + K6
+    bool decode(const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
+                std::vector<SampleResult>& results, float* logits_host) override {
+        CUDA_OK(cudaSetDevice(device_));
+        results.resize(sample_rows.size());
+        if (rows.empty()) return true;
+        if (sp.size() != sample_rows.size()) { err_ = "decode: params/sample size mismatch"; return false; }
+        CUDA_OK(cudaEventRecord(ev_[0], stream_));
+        size_t si = 0;
+        for (size_t r0 = 0; r0 < rows.size();) {
+            // a chunk holds at most dec_rows_ rows and dec_samples_ sample rows
+            size_t r1 = std::min(rows.size(), r0 + (size_t)dec_rows_);
+            size_t sj = si;
+            while (sj < sample_rows.size() && (size_t)sample_rows[sj] < r1) {
+                if (sj - si == (size_t)dec_samples_) { r1 = (size_t)sample_rows[sj]; break; }
+                ++sj;
+            }
+            if (r1 == r0) { err_ = "decode: cannot make progress"; return false; }
+            if (!decode_chunk(rows.data() + r0, (int)(r1 - r0), sample_rows.data() + si, (int)(sj - si), (int)r0, sp.data() + si,
+                              results.data() + si, logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr))
+                return false;
+            si = sj;
+            r0 = r1;
+        }
+        CUDA_OK(cudaEventRecord(ev_[1], stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        stats.ms_decode += ms;
+        return true;
+    }
+
+    bool decode_chunk(const RowDesc* rows, int R, const int* samp, int S, int row_base, const SampleParams* sp, SampleResult* res,
+                      float* logits_host) {
+        const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        for (int r = 0; r < R; ++r) {
+            const RowDesc& rd = rows[r];
+            if (rd.token < 0 || rd.token >= hp_.n_vocab || rd.pos < 0 || rd.pos >= ntc || rd.kv_slot < 0 || rd.kv_slot >= kv_cap_ ||
+                rd.audio_slot < 0 || rd.audio_slot >= audio_cap_) { err_ = "decode: bad row"; return false; }
+        }
+        const size_t rows_bytes = align_up(sizeof(RowDesc) * R, 256), idx_bytes = align_up(sizeof(int) * std::max(S, 1), 256);
+        const size_t sp_bytes = align_up(sizeof(SampleParams) * std::max(S, 1), 256), res_bytes = align_up(sizeof(SampleResult) * std::max(S, 1), 256);
+        if (!ensure_pin(rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
+        if (!ensure_dev_scratch(rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
+        CUDA_OK(cudaStreamSynchronize(stream_));  // pinned staging reuse
+        char* hp = pin_;
+        memcpy(hp, rows, sizeof(RowDesc) * R);
+        int* hidx = reinterpret_cast<int*>(hp + rows_bytes);
+        for (int i = 0; i < S; ++i) hidx[i] = samp[i] - row_base;
+        if (S) memcpy(hp + rows_bytes + idx_bytes, sp, sizeof(SampleParams) * S);
+        CUDA_OK(cudaMemcpyAsync(dev_scratch_, hp, rows_bytes + idx_bytes + sp_bytes, cudaMemcpyHostToDevice, stream_));
+        const RowDesc* drows = reinterpret_cast<const RowDesc*>(dev_scratch_);
+        const int* didx = reinterpret_cast<const int*>(dev_scratch_ + rows_bytes);
+        const SampleParams* dsp = reinterpret_cast<const SampleParams*>(dev_scratch_ + rows_bytes + idx_bytes);
+        SampleResult* dres = reinterpret_cast<SampleResult*>(dev_scratch_ + rows_bytes + idx_bytes + sp_bytes);
+
+        launch_embed<T>(drows, R, tok_emb_, dec_pos_, d_x_, d, stream_);
+        const size_t self_layer = (size_t)2 * ntc * d;             // [K|V][448][d]
+        const size_t self_slot = (size_t)Ld * self_layer;
+        const size_t cross_pos = (size_t)2 * Ld * d;               // position stride in the cross pool
+        const size_t cross_slot = (size_t)kWinRows * cross_pos;
+        for (int l = 0; l < Ld; ++l) {
+            const Layer<T>& L = dec_[l];
+            launch_layernorm<T>(d_x_, d, L.ln1_g, L.ln1_b, d_y_, d, R, d, stream_);
+            { Epilogue e; e.bias = L.bqkv; if (!gemm(d_y_, d, L.wqkv, d, d_qkv_, 3 * d, R, 3 * d, d, e, stream_)) return gemm_fail(); }
+            T* kc = self_pool_ + (size_t)l * self_layer;
+            T* vc = kc + (size_t)ntc * d;
+            launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, d, stream_);
+            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, (size_t)d, 0, stream_);
+            { Epilogue e; e.bias = L.bo; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wo, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
+            launch_layernorm<T>(d_x_, d, L.lnc_g, L.lnc_b, d_y_, d, R, d, stream_);
+            { Epilogue e; e.bias = L.bcq; if (!gemm(d_y_, d, L.wcq, d, d_qkv_, d, R, d, d, e, stream_)) return gemm_fail(); }
+            const T* ck = cross_pool_ + (size_t)l * 2 * d;
+            const T* cv = ck + d;
+            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_pos, hp_.n_audio_ctx, stream_);
+            { Epilogue e; e.bias = L.bco; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wco, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
+            launch_layernorm<T>(d_x_, d, L.ln2_g, L.ln2_b, d_y_, d, R, d, stream_);
+            { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(d_y_, d, L.w1, d, d_h_, 4 * d, R, 4 * d, d, e, stream_)) return gemm_fail(); }
+            { Epilogue e; e.bias = L.b2; e.res = d_x_; e.res_ld = d; if (!gemm(d_h_, 4 * d, L.w2, 4 * d, d_x_, d, R, d, 4 * d, e, stream_)) return gemm_fail(); }
+        }
+        if (S > 0) {
+            launch_layernorm_gather<T>(d_x_, d, didx, dec_ln_g_, dec_ln_b_, d_ys_, d, S, d, stream_);
+            { Epilogue e; if (!gemm(d_ys_, d, tok_emb_, d, d_logits_, hp_.n_vocab, S, hp_.n_vocab, d, e, stream_)) return gemm_fail(); }
+            launch_process_logits(d_logits_, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, nullptr, stream_);
+            CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, stream_));
+            if (logits_host)
+                CUDA_OK(cudaMemcpyAsync(logits_host, d_logits_, sizeof(float) * (size_t)S * hp_.n_vocab, cudaMemcpyDeviceToHost, stream_));
+        }
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaGetLastError());
+        if (S > 0) memcpy(res, hp + rows_bytes + idx_bytes + sp_bytes, sizeof(SampleResult) * S);
+        last_logit_rows_ = S;
+        return true;
+    }
+
+    bool lang_probs(int sample_index, float* probs_host, int* best) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (sample_index < 0 || sample_index >= last_logit_rows_) { err_ = "lang_probs: no such logits row"; return false; }
+        if (!ensure_dev_scratch(1024)) return false;
+        float* dp = reinterpret_cast<float*>(dev_scratch_);
+        int* db = reinterpret_cast<int*>(dev_scratch_ + 512);
+        launch_lang_probs(d_logits_ + (size_t)sample_index * hp_.n_vocab, vocab_ids, dp, db, stream_);
+        float hp[kNumLangs];
+        CUDA_OK(cudaMemcpyAsync(hp, dp, sizeof(hp), cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaMemcpyAsync(best, db, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        if (probs_host) memcpy(probs_host, hp, sizeof(hp));
+        return true;
+    }
+
+    bool kv_copy(const std::vector<KvCopy>& pairs) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (pairs.empty()) return true;
+        const size_t bytes = sizeof(KvCopy) * pairs.size();
+        if (!ensure_pin(bytes) || !ensure_dev_scratch(bytes)) return false;
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        memcpy(pin_, pairs.data(), bytes);
+        CUDA_OK(cudaMemcpyAsync(dev_scratch_, pin_, bytes, cudaMemcpyHostToDevice, stream_));
+        const int d = d_, ntc = hp_.n_text_ctx, Ld = hp_.n_text_layer;
+        launch_kv_copy<T>(reinterpret_cast<const KvCopy*>(dev_scratch_), (int)pairs.size(), self_pool_, (size_t)Ld * 2 * ntc * d, 2 * Ld,
+                          (size_t)ntc * d, d, stream_);
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+
+    bool process_logits_host(const float* logits, const SampleParams& sp, SampleResult& out, float* logprobs, float* probs) override {
+        CUDA_OK(cudaSetDevice(device_));
+        const int nv = hp_.n_vocab;
+        const size_t lbytes = align_up(sizeof(float) * nv, 256);
+        if (!ensure_dev_scratch(3 * lbytes + 1024)) return false;
+        float* dl = reinterpret_cast<float*>(dev_scratch_);
+        float* dlp = reinterpret_cast<float*>(dev_scratch_ + lbytes);
+        float* dpr = reinterpret_cast<float*>(dev_scratch_ + 2 * lbytes);
+        SampleParams* dsp = reinterpret_cast<SampleParams*>(dev_scratch_ + 3 * lbytes);
+        SampleResult* dres = reinterpret_cast<SampleResult*>(dev_scratch_ + 3 * lbytes + 256);
+        CUDA_OK(cudaMemcpyAsync(dl, logits, sizeof(float) * nv, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaMemcpyAsync(dsp, &sp, sizeof(sp), cudaMemcpyHostToDevice, stream_));
+        launch_process_logits(dl, nv, dsp, dres, 1, vocab_ids, dlp, dpr, stream_);
+        CUDA_OK(cudaMemcpyAsync(&out, dres, sizeof(out), cudaMemcpyDeviceToHost, stream_));
+        if (logprobs) CUDA_OK(cudaMemcpyAsync(logprobs, dlp, sizeof(float) * nv, cudaMemcpyDeviceToHost, stream_));
+        if (probs) CUDA_OK(cudaMemcpyAsync(probs, dpr, sizeof(float) * nv, cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaGetLastError());
+        return true;
+    }
+
+    // ------------------------------------------------------------------ inspection
+    bool export_mel(const DeviceMel& m, float* out) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (!m.raw) { err_ = "no mel"; return false; }
+        const size_t n = (size_t)m.n_len * m.n_mel;
+        if (!ensure_dev_scratch(n * sizeof(float))) return false;
+        launch_export_mel(m.raw, m.max_key, m.n_frames, m.n_len, m.n_mel, reinterpret_cast<float*>(dev_scratch_), stream_);
+        CUDA_OK(cudaMemcpyAsync(out, dev_scratch_, n * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+    bool export_encoder_output(int slot, float* out) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (slot < 0 || slot >= audio_cap_) { err_ = "bad slot"; return false; }
+        const int n = hp_.n_audio_ctx;
+        if (!ensure_dev_scratch((size_t)n * d_ * sizeof(float))) return false;
+        launch_convert_2d<T, float>(encout_pool_ + (size_t)slot * kWinRows * d_, d_, reinterpret_cast<float*>(dev_scratch_), d_, n, d_, stream_);
+        CUDA_OK(cudaMemcpyAsync(out, dev_scratch_, (size_t)n * d_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+    bool export_cross_kv(int slot, int layer, float* k, float* v) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (slot < 0 || slot >= audio_cap_ || layer < 0 || layer >= hp_.n_text_layer) { err_ = "bad slot/layer"; return false; }
+        const int n = hp_.n_audio_ctx;
+        const size_t ldx = (size_t)2 * hp_.n_text_layer * d_;
+        const size_t bytes = (size_t)n * d_ * sizeof(float);
+        if (!ensure_dev_scratch(2 * bytes)) return false;
+        const T* base = cross_pool_ + (size_t)slot * kWinRows * ldx + (size_t)layer * 2 * d_;
+        float* dk = reinterpret_cast<float*>(dev_scratch_);
+        float* dv = reinterpret_cast<float*>(dev_scratch_ + bytes);
+        launch_convert_2d<T, float>(base, ldx, dk, d_, n, d_, stream_);
+        launch_convert_2d<T, float>(base + d_, ldx, dv, d_, n, d_, stream_);
+        CUDA_OK(cudaMemcpyAsync(k, dk, bytes, cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaMemcpyAsync(v, dv, bytes, cudaMemcpyDeviceToHost, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+
+private:
+    bool gemm_fail() {
+        if (err_.empty()) err_ = std::string("GEMM launch failed: ") + sm100_last_error();
+        return false;
+    }
+    bool ensure_pin(size_t bytes) {
+        if (bytes <= pin_cap_) return true;
+        if (pin_) { CUDA_OK(cudaStreamSynchronize(stream_)); CUDA_OK(cudaFreeHost(pin_)); pin_ = nullptr; }
+        pin_cap_ = align_up(bytes * 2, 1 << 16);
+        CUDA_OK(cudaMallocHost(&pin_, pin_cap_));
+        return true;
+    }
+    bool ensure_dev_scratch(size_t bytes) {
+        if (bytes <= dev_scratch_cap_) return true;
+        if (dev_scratch_) { CUDA_OK(cudaStreamSynchronize(stream_)); CUDA_OK(cudaFree(dev_scratch_)); dev_scratch_ = nullptr; }
+        dev_scratch_cap_ = align_up(bytes * 2, 1 << 16);
+        CUDA_OK(cudaMalloc(&dev_scratch_, dev_scratch_cap_));
+        return true;
+    }
+    bool take_cached_mel(DeviceMel& m, size_t need) {
+        for (size_t i = 0; i < mel_cache_.size(); ++i)
+            if (mel_cache_[i].raw_cap >= need) {
+                const DeviceMel c = mel_cache_[i];
+                mel_cache_.erase(mel_cache_.begin() + i);
+                m.raw = c.raw; m.max_key = c.max_key; m.raw_cap = c.raw_cap;
+                return true;
+            }
+        return false;
+    }
+    template <typename P>
+    bool grow_pool(P*& pool, int old_cap, int new_cap, size_t slot_elems) {
+        P* np = nullptr;
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaMalloc(&np, (size_t)new_cap * slot_elems * sizeof(P)));
+        if (pool && old_cap > 0) CUDA_OK(cudaMemcpy(np, pool, (size_t)old_cap * slot_elems * sizeof(P), cudaMemcpyDeviceToDevice));
+        if (pool) CUDA_OK(cudaFree(pool));
+        pool = np;
+        return true;
+    }
+    bool grow_audio(int new_cap) {
+        const size_t cross_slot = (size_t)kWinRows * 2 * hp_.n_text_layer * d_;
+        if (!grow_pool(cross_pool_, audio_cap_, new_cap, cross_slot)) return false;
+        if (!grow_pool(encout_pool_, audio_cap_, new_cap, (size_t)kWinRows * d_)) return false;
+        for (int s = new_cap - 1; s >= audio_cap_; --s) audio_free_.push_back(s);
+        audio_cap_ = new_cap;
+        return true;
+    }
+    bool grow_kv(int new_cap) {
+        const size_t slot = (size_t)hp_.n_text_layer * 2 * hp_.n_text_ctx * d_;
+        if (!grow_pool(self_pool_, kv_cap_, new_cap, slot)) return false;
+        for (int s = new_cap - 1; s >= kv_cap_; --s) kv_free_.push_back(s);
+        kv_cap_ = new_cap;
+        return true;
+    }
+
+    // weights ------------------------------------------------------------------------------
+    struct Arena {
+        char* base = nullptr;
+        size_t cap = 0, used = 0;
+        void* take(size_t bytes) {
+            used = align_up(used, 256);
+            void* p = base ? base + used : nullptr;
+            used += bytes;
+            return p;
+        }
+    };
+    template <typename P>
+    P* put(Arena& a, const std::vector<float>& host) {  // upload as fp32 then convert to P on the device
+        P* dst = reinterpret_cast<P*>(a.take(host.size() * sizeof(P)));
+        if (!a.base) return dst;  // sizing pass
+        upload_ok_ = upload_ok_ && upload_convert(host.data(), host.size(), dst);
+        return dst;
+    }
+    bool upload_convert(const float* src, size_t n, float* dst) {
+        CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        return true;
+    }
+    bool upload_convert(const float* src, size_t n, bf16* dst) {
+        const size_t chunk = (size_t)32 << 20;  // floats
+        if (!ensure_dev_scratch(std::min(n, chunk) * sizeof(float))) return false;
+        for (size_t o = 0; o < n; o += chunk) {
+            const size_t c = std::min(chunk, n - o);
+            CUDA_OK(cudaMemcpyAsync(dev_scratch_, src + o, c * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            launch_convert<float, bf16>(reinterpret_cast<const float*>(dev_scratch_), dst + o, c, stream_);
+            CUDA_OK(cudaStreamSynchronize(stream_));
+        }
+        return true;
+    }
+
+    static std::vector<float> concat(std::initializer_list<const std::vector<float>*> parts) {
+        std::vector<float> out;
+        for (auto* p : parts) out.insert(out.end(), p->begin(), p->end());
+        return out;
+    }
+
+    void build_weights(const HostModel& hm, Arena& a) {
+        const int d = d_, nm = hp_.n_mels;
+        auto W = [&](const std::string& n) -> const std::vector<float>& { return hm.get(n).data; };
+        const std::vector<float> zeros_d(d, 0.0f);
+        // conv weights [o][c][k] -> [o][(k, c)] so a row of the im2col-free operand (3 consecutive
+        // time steps x channels) lines up with a weight row
+        auto reorder_conv = [&](const std::vector<float>& w, int cin) {
+            std::vector<float> r((size_t)d * 3 * cin);
+            for (int o = 0; o < d; ++o)
+                for (int c = 0; c < cin; ++c)
+                    for (int k = 0; k < 3; ++k) r[((size_t)o * 3 + k) * cin + c] = w[((size_t)o * cin + c) * 3 + k];
+            return r;
+        };
+        conv1_w_ = put<T>(a, reorder_conv(W("encoder.conv1.weight"), nm));
+        conv1_b_ = put<float>(a, W("encoder.conv1.bias"));
+        conv2_w_ = put<T>(a, reorder_conv(W("encoder.conv2.weight"), d));
+        conv2_b_ = put<float>(a, W("encoder.conv2.bias"));
+        {
+            std::vector<float> pe((size_t)kWinRows * d, 0.0f);
+            const auto& src = W("encoder.positional_embedding");
+            std::copy(src.begin(), src.end(), pe.begin());
+            enc_pos_ = put<float>(a, pe);
+        }
+        auto attn = [&](const std::string& p, Layer<T>& L, bool self) {
+            if (self) {
+                L.ln1_g = put<float>(a, W(p + "_ln.weight"));
+                L.ln1_b = put<float>(a, W(p + "_ln.bias"));
+                L.wqkv = put<T>(a, concat({&W(p + ".query.weight"), &W(p + ".key.weight"), &W(p + ".value.weight")}));
+                L.bqkv = put<float>(a, concat({&W(p + ".query.bias"), &zeros_d, &W(p + ".value.bias")}));
+                L.wo = put<T>(a, W(p + ".out.weight"));
+                L.bo = put<float>(a, W(p + ".out.bias"));
+            } else {
+                L.lnc_g = put<float>(a, W(p + "_ln.weight"));
+                L.lnc_b = put<float>(a, W(p + "_ln.bias"));
+                L.wcq = put<T>(a, W(p + ".query.weight"));
+                L.bcq = put<float>(a, W(p + ".query.bias"));
+                L.wco = put<T>(a, W(p + ".out.weight"));
+                L.bco = put<float>(a, W(p + ".out.bias"));
+            }
+        };
+        auto mlp = [&](const std::string& p, Layer<T>& L) {
+            L.ln2_g = put<float>(a, W(p + "mlp_ln.weight"));
+            L.ln2_b = put<float>(a, W(p + "mlp_ln.bias"));
+            L.w1 = put<T>(a, W(p + "mlp.0.weight"));
+            L.b1 = put<float>(a, W(p + "mlp.0.bias"));
+            L.w2 = put<T>(a, W(p + "mlp.2.weight"));
+            L.b2 = put<float>(a, W(p + "mlp.2.bias"));
+        };
+        enc_.assign(hp_.n_audio_layer, Layer<T>());
+        for (int i = 0; i < hp_.n_audio_layer; ++i) {
+            const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+            attn(p + "attn", enc_[i], true);
+            mlp(p, enc_[i]);
+        }
+        enc_lnp_g_ = put<float>(a, W("encoder.ln_post.weight"));
+        enc_lnp_b_ = put<float>(a, W("encoder.ln_post.bias"));
+        dec_.assign(hp_.n_text_layer, Layer<T>());
+        std::vector<float> cw, cb;
+        if (a.base) { cw.reserve((size_t)2 * hp_.n_text_layer * d * d); cb.reserve((size_t)2 * hp_.n_text_layer * d); }
+        for (int i = 0; i < hp_.n_text_layer; ++i) {
+            const std::string p = "decoder.blocks." + std::to_string(i) + ".";
+            attn(p + "attn", dec_[i], true);
+            attn(p + "cross_attn", dec_[i], false);
+            mlp(p, dec_[i]);
+            if (a.base) {
+                const auto& k = W(p + "cross_attn.key.weight");
+                const auto& v = W(p + "cross_attn.value.weight");
+                cw.insert(cw.end(), k.begin(), k.end());
+                cw.insert(cw.end(), v.begin(), v.end());
+                cb.insert(cb.end(), zeros_d.begin(), zeros_d.end());
+                const auto& vb = W(p + "cross_attn.value.bias");
+                cb.insert(cb.end(), vb.begin(), vb.end());
+            }
+        }
+        if (!a.base) { cw.resize((size_t)2 * hp_.n_text_layer * d * d); cb.resize((size_t)2 * hp_.n_text_layer * d); }
+        cross_w_ = put<T>(a, cw);
+        cross_b_ = put<float>(a, cb);
+        dec_ln_g_ = put<float>(a, W("decoder.ln.weight"));
+        dec_ln_b_ = put<float>(a, W("decoder.ln.bias"));
+        dec_pos_ = put<float>(a, W("decoder.positional_embedding"));
+        tok_emb_ = put<T>(a, W("decoder.token_embedding.weight"));
+    }
+
+    bool upload_weights(const HostModel& hm) {
+        try {
+            Arena sizing;
+            build_weights(hm, sizing);
+            Arena a;
+            a.cap = align_up(sizing.used, 256) + 256;
+            CUDA_OK(cudaMalloc(&a.base, a.cap));
+            owned_.push_back(a.base);
+            upload_ok_ = true;
+            build_weights(hm, a);
+            if (!upload_ok_) return false;
+            weight_bytes_ = a.used;
+        } catch (const std::exception& e) {
+            err_ = e.what();
+            return false;
+        }
+        // mel tables
+        std::vector<float> hann(kNFft);
+        std::vector<float2> tw(kNFft);
+        for (int i = 0; i < kNFft; ++i) {
+            const double th = 2.0 * M_PI * i / kNFft;
+            hann[i] = (float)(0.5 * (1.0 - cos(th)));
+            tw[i] = make_float2((float)cos(th), (float)sin(th));
+        }
+        std::vector<int2> ranges(hp_.n_mels);
+        for (int m = 0; m < hp_.n_mels; ++m) {
+            int lo = kNFreq, hi = 0;
+            for (int k = 0; k < kNFreq; ++k)
+                if (hm.filters[(size_t)m * kNFreq + k] != 0.0f) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+            if (lo > hi) lo = hi = 0;
+            ranges[m] = make_int2(lo, hi);
+        }
+        float *dh, *df; float2* dt; int2* dr;
+        CUDA_OK(cudaMalloc(&dh, sizeof(float) * kNFft)); owned_.push_back(dh);
+        CUDA_OK(cudaMalloc(&dt, sizeof(float2) * kNFft)); owned_.push_back(dt);
+        CUDA_OK(cudaMalloc(&df, sizeof(float) * hm.filters.size())); owned_.push_back(df);
+        CUDA_OK(cudaMalloc(&dr, sizeof(int2) * ranges.size())); owned_.push_back(dr);
+        CUDA_OK(cudaMemcpy(dh, hann.data(), sizeof(float) * kNFft, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(dt, tw.data(), sizeof(float2) * kNFft, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(df, hm.filters.data(), sizeof(float) * hm.filters.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(dr, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice));
+        mel_tables_ = MelTables{dh, dt, df, dr, hp_.n_mels};
+        return true;
+    }
+
+    bool alloc_workspace() {
+        const int d = d_, nm = hp_.n_mels;
+        const bool f32 = sizeof(T) == 4;
+        enc_batch_ = std::max(1, env_int("NOBS_WHISPER_ENC_BATCH", f32 ? 2 : 8));
+        dec_rows_ = std::max(64, env_int("NOBS_WHISPER_DEC_ROWS", 4096));
+        dec_samples_ = std::max(8, env_int("NOBS_WHISPER_DEC_SAMPLES", 1024));
+        // encoder and decoder never run concurrently: both views alias one arena
+        Arena e;
+        auto plan_enc = [&](Arena& a) {
+            const size_t M = (size_t)enc_batch_ * kWinRows;
+            e_mel_ = (T*)a.take(((size_t)enc_batch_ * kWinRowsIn + 2) * nm * sizeof(T));
+            e_h1_ = (T*)a.take(((size_t)enc_batch_ * kWinRowsIn + 1) * d * sizeof(T));
+            e_x_ = (float*)a.take(M * d * sizeof(float));
+            e_y_ = (T*)a.take(M * d * sizeof(T));
+            e_qkv_ = (T*)a.take(M * 3 * d * sizeof(T));
+            e_att_ = (T*)a.take(M * d * sizeof(T));
+            e_h_ = (T*)a.take(M * 4 * d * sizeof(T));
+        };
+        auto plan_dec = [&](Arena& a) {
+            const size_t R = dec_rows_, S = dec_samples_;
+            d_x_ = (float*)a.take(R * d * sizeof(float));
+            d_y_ = (T*)a.take(R * d * sizeof(T));
+            d_qkv_ = (T*)a.take(R * 3 * d * sizeof(T));
+            d_att_ = (T*)a.take(R * d * sizeof(T));
+            d_h_ = (T*)a.take(R * 4 * d * sizeof(T));
+            d_ys_ = (T*)a.take(S * d * sizeof(T));
+            d_logits_ = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
+        };
+        Arena se, sd;
+        plan_enc(se);
+        plan_dec(sd);
+        const size_t bytes = std::max(se.used, sd.used) + 512;
+        char* base = nullptr;
+        CUDA_OK(cudaMalloc(&base, bytes));
+        owned_.push_back(base);
+        CUDA_OK(cudaMemset(base, 0, bytes));
+        Arena ae; ae.base = base; ae.cap = bytes;
+        Arena ad = ae;
+        plan_enc(ae);
+        plan_dec(ad);
+        ws_base_ = base;
+        ws_bytes_ = bytes;
+        return true;
+    }
+
+    // the conv operands rely on zero rows that only the encoder view keeps zero: rows 0 / last
+    // of e_mel_ and row 0 of e_h1_.  The decoder view aliases the same memory, so they are
+    // re-zeroed at the start of every encode batch.
+public:
+    bool rezero_conv_pads(int nb) {
+        const int d = d_, nm = hp_.n_mels;
+        CUDA_OK(cudaMemsetAsync(e_mel_, 0, (size_t)nm * sizeof(T), stream_));
+        CUDA_OK(cudaMemsetAsync(e_mel_ + ((size_t)nb * kWinRowsIn + 1) * nm, 0, (size_t)nm * sizeof(T), stream_));
+        CUDA_OK(cudaMemsetAsync(e_h1_, 0, (size_t)d * sizeof(T), stream_));
+        return true;
+    }
+
+private:
+    HParams hp_;
+    int d_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    std::vector<void*> owned_;
+    size_t weight_bytes_ = 0;
+    bool upload_ok_ = true;
+    const int init_key_ = INT_MIN;
+
+    // weights
+    T *conv1_w_ = nullptr, *conv2_w_ = nullptr, *cross_w_ = nullptr, *tok_emb_ = nullptr;
+    float *conv1_b_ = nullptr, *conv2_b_ = nullptr, *enc_pos_ = nullptr, *cross_b_ = nullptr, *dec_pos_ = nullptr;
+    float *enc_lnp_g_ = nullptr, *enc_lnp_b_ = nullptr, *dec_ln_g_ = nullptr, *dec_ln_b_ = nullptr;
+    std::vector<Layer<T>> enc_, dec_;
+    MelTables mel_tables_{};
+
+    // pools
+    T *cross_pool_ = nullptr, *self_pool_ = nullptr, *encout_pool_ = nullptr;
+    int audio_cap_ = 0, kv_cap_ = 0;
+    std::vector<int> audio_free_, kv_free_;
+    std::vector<DeviceMel> mel_cache_;
+
+    // workspaces
+    int enc_batch_ = 1, dec_rows_ = 0, dec_samples_ = 0;
+    char* ws_base_ = nullptr;
+    size_t ws_bytes_ = 0;
+    T *e_mel_ = nullptr, *e_h1_ = nullptr, *e_y_ = nullptr, *e_qkv_ = nullptr, *e_att_ = nullptr, *e_h_ = nullptr;
+    float* e_x_ = nullptr;
+    float* d_x_ = nullptr;
+    T *d_y_ = nullptr, *d_qkv_ = nullptr, *d_att_ = nullptr, *d_h_ = nullptr, *d_ys_ = nullptr;
+    float* d_logits_ = nullptr;
+    int last_logit_rows_ = 0;
+
+    char* pin_ = nullptr;
+    size_t pin_cap_ = 0;
+    char* dev_scratch_ = nullptr;
+    size_t dev_scratch_cap_ = 0;
+    float* pcm_dev_ = nullptr;
+    size_t pcm_cap_ = 0;
+};
+
+}  // namespace
+
+Engine* Engine::create(const HostModel& hm, int device, Precision prec, std::string& err) {
+    if (prec == Precision::FP32) {
+        auto* e = new EngineT<float>(hm, device, prec);
+        if (!e->init(hm)) { err = e->last_error(); delete e; return nullptr; }
+        return e;
+    }
+    auto* e = new EngineT<bf16>(hm, device, prec);
+    if (!e->init(hm)) { err = e->last_error(); delete e; return nullptr; }
+    return e;
+}
+
+}  // namespace nobs

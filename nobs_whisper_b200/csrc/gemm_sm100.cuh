@@ -1,0 +1,16 @@
+// tcgen05 / TMEM / TMA kernels for the bf16 production path (sm_100a only).
+#pragma once
+#include "kernels.cuh"
+
+namespace nobs {
+
+// C[M,N] = epi(A[M,K] * W[N,K]^T): bf16 operands (K-contiguous), fp32 accumulation in TMEM,
+// C written as bf16 or fp32.  Returns false (see sm100_last_error) if a tensor map cannot be
+// encoded or the launch fails.
+bool launch_gemm_bf16_sm100(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, bool c_is_f32, int M, int N, int K,
+                            const Epilogue& e, cudaStream_t s);
+// Non-causal encoder self-attention over 1500 keys per window, head size 64.
+bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s);
+const char* sm100_last_error();
+
+}  // namespace nobs

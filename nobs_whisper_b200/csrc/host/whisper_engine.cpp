@@ -1,0 +1,312 @@
+#include "whisper_engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace nobs {
+
+std::string WhisperError::to_string() const {
+    switch (kind) {
+        case LoadError: return "Failed to load model: " + message;
+        case TranscriptionError: return "Transcription failed: " + message;
+        case NoModel: return "No model loaded";
+        default: return "";
+    }
+}
+
+namespace {
+
+// reference whisper.rs:202-230 (data: the phrases whose exact match is discarded)
+const char* const kHallucinationPhrases[] = {
+    "thank you for watching", "thanks for watching", "thank you for listening", "thanks for listening",
+    "subscribe to my channel", "please subscribe", "like and subscribe", "see you in the next video",
+    "see you next time", "please like and subscribe", "don't forget to subscribe", "hit the bell",
+    "leave a comment", "check out my other videos", "thanks for tuning in",
+    "시청해 주셔서 감사합니다", "구독과 좋아요", "구독 부탁드립니다",
+    "ご視聴ありがとうございました",
+    "感谢收看", "谢谢观看",
+    "you", "MBC 뉴스 이덕영입니다",
+};
+
+// decode one UTF-8 scalar starting at s[i]; returns its byte length (1 on malformed input)
+size_t utf8_len(const std::string& s, size_t i) {
+    const unsigned char c = (unsigned char)s[i];
+    size_t n = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 1;
+    if (i + n > s.size()) n = 1;
+    return n;
+}
+bool is_ascii_punct(unsigned char c) { return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126); }
+// Rust char::is_whitespace for the characters that can realistically appear (ASCII + common Unicode spaces)
+size_t whitespace_len_at(const std::string& s, size_t i) {
+    const unsigned char c = (unsigned char)s[i];
+    if (c == ' ' || (c >= 9 && c <= 13)) return 1;
+    if (c == 0xC2 && i + 1 < s.size() && ((unsigned char)s[i + 1] == 0x85 || (unsigned char)s[i + 1] == 0xA0)) return 2;
+    if (c == 0xE2 && i + 2 < s.size()) {
+        const unsigned char b1 = (unsigned char)s[i + 1], b2 = (unsigned char)s[i + 2];
+        if (b1 == 0x80 && ((b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF)) return 3;
+        if (b1 == 0x81 && b2 == 0x9F) return 3;
+    }
+    if (c == 0xE3 && i + 2 < s.size() && (unsigned char)s[i + 1] == 0x80 && (unsigned char)s[i + 2] == 0x80) return 3;
+    if (c == 0xE1 && i + 2 < s.size() && (unsigned char)s[i + 1] == 0x9A && (unsigned char)s[i + 2] == 0x80) return 3;
+    return 0;
+}
+std::string trim(const std::string& s) {
+    size_t b = 0, e = s.size();
+    while (b < e) { size_t l = whitespace_len_at(s, b); if (!l) break; b += l; }
+    while (e > b) {
+        // step back one scalar
+        size_t p = e - 1;
+        while (p > b && ((unsigned char)s[p] & 0xC0) == 0x80) --p;
+        if (whitespace_len_at(s, p) == e - p && e - p > 0) e = p; else break;
+    }
+    return s.substr(b, e - b);
+}
+// symbols the reference treats like punctuation: '…' U+2026, '♪' U+266A, U+266B, U+266C
+bool is_music_or_ellipsis(const std::string& s, size_t i, size_t n, bool with_beamed) {
+    if (n != 3) return false;
+    const unsigned char a = (unsigned char)s[i], b = (unsigned char)s[i + 1], c = (unsigned char)s[i + 2];
+    if (a == 0xE2 && b == 0x80 && c == 0xA6) return true;               // …
+    if (a == 0xE2 && b == 0x99 && c == 0xAA) return true;               // ♪
+    if (with_beamed && a == 0xE2 && b == 0x99 && (c == 0xAB || c == 0xAC)) return true;
+    return false;
+}
+// ASCII lower-casing plus the two-byte Latin-1/Greek/Cyrillic upper-case ranges is all the phrase list needs
+// (the CJK / Hangul phrases have no case).
+std::string to_lower(const std::string& s) {
+    std::string o = s;
+    for (auto& ch : o) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+    return o;
+}
+
+}  // namespace
+
+std::string filter_hallucinations(const std::string& text) {
+    const std::string trimmed = trim(text);
+    if (trimmed.empty()) return std::string();
+    // punctuation / symbol only output ("...", "♪") is discarded   (whisper.rs:240-243)
+    {
+        bool all = true;
+        for (size_t i = 0; i < trimmed.size();) {
+            const size_t n = utf8_len(trimmed, i);
+            if (!((n == 1 && is_ascii_punct((unsigned char)trimmed[i])) || is_music_or_ellipsis(trimmed, i, n, true))) { all = false; break; }
+            i += n;
+        }
+        if (all) return std::string();
+    }
+    const std::string lower = to_lower(trimmed);
+    // strip trailing punctuation (ASCII, '…', '♪') then compare with each phrase   (whisper.rs:248-257)
+    size_t e = lower.size();
+    while (e > 0) {
+        size_t p = e - 1;
+        while (p > 0 && ((unsigned char)lower[p] & 0xC0) == 0x80) --p;
+        const size_t n = e - p;
+        if ((n == 1 && is_ascii_punct((unsigned char)lower[p])) || is_music_or_ellipsis(lower, p, n, false)) e = p; else break;
+    }
+    const std::string stripped = lower.substr(0, e);
+    for (const char* phrase : kHallucinationPhrases)
+        if (stripped == to_lower(phrase)) return std::string();
+    return trimmed;
+}
+
+WhisperEngine::~WhisperEngine() { unload_model(); }
+
+WhisperError WhisperEngine::load_model(const std::string& model_path) {
+    whisper_context_params cp = whisper_context_default_params();
+    cp.use_gpu = true;  // whisper.rs:40
+    whisper_context* c = whisper_init_from_file_with_params_no_state(model_path.c_str(), cp);
+    if (!c) {
+        const char* e = whisper_b200_last_error();
+        return WhisperError{WhisperError::LoadError, (e && *e) ? e : "failed to initialise whisper context"};
+    }
+    unload_model();
+    ctx_ = c;
+    model_path_ = model_path;
+    return WhisperError{};
+}
+
+void WhisperEngine::unload_model() {
+    if (ctx_) whisper_free(ctx_);
+    ctx_ = nullptr;
+    model_path_.clear();
+}
+
+std::optional<std::string> WhisperEngine::build_prompt(const std::optional<std::string>& vocabulary, const std::optional<std::string>& context) {
+    // whisper.rs:98-105
+    if (vocabulary && context && !vocabulary->empty()) return *vocabulary + " " + *context;
+    if (vocabulary && !context && !vocabulary->empty()) return *vocabulary;
+    if (context) return *context;
+    return std::nullopt;
+}
+
+whisper_full_params WhisperEngine::make_params(const std::optional<std::string>& language, const std::string* initial_prompt, int beam_size) const {
+    whisper_full_params p;
+    if (beam_size > 0) {
+        p = whisper_full_default_params(WHISPER_SAMPLING_BEAM_SEARCH);
+        p.beam_search.beam_size = beam_size;
+        p.beam_search.patience = -1.0f;
+    } else {
+        p = whisper_full_default_params(WHISPER_SAMPLING_GREEDY);
+        p.greedy.best_of = 1;  // whisper.rs:88
+    }
+    p.language = language ? language->c_str() : nullptr;                 // whisper.rs:91-95 (None => auto-detect)
+    if (initial_prompt) p.initial_prompt = initial_prompt->c_str();      // whisper.rs:106-107
+    p.print_special = false;                                             // whisper.rs:112-118
+    p.print_progress = false;
+    p.print_realtime = false;
+    p.print_timestamps = false;
+    p.translate = false;
+    p.no_context = false;
+    p.single_segment = false;
+    p.suppress_blank = true;                                             // whisper.rs:121-124
+    p.no_speech_thold = 0.6f;
+    p.entropy_thold = 2.4f;
+    p.logprob_thold = -1.0f;
+    return p;
+}
+
+static std::string collect_text(whisper_state* st) {
+    // whisper.rs:132-141: concatenate segment texts with no separator
+    std::string result;
+    const int n = whisper_full_n_segments_from_state(st);
+    for (int i = 0; i < n; ++i) {
+        const char* t = whisper_full_get_segment_text_from_state(st, i);
+        if (t) result += t;
+    }
+    return result;
+}
+
+WhisperError WhisperEngine::transcribe(const float* audio, int n, const std::optional<std::string>& language,
+                                       const std::optional<std::string>& vocabulary, const std::optional<std::string>& context,
+                                       std::string& out) const {
+    out.clear();
+    if (!ctx_) return WhisperError{WhisperError::NoModel, ""};                      // whisper.rs:73
+    whisper_state* st = whisper_init_state(ctx_);                                    // whisper.rs:83-85
+    if (!st) return WhisperError{WhisperError::TranscriptionError, whisper_b200_last_error()};
+    const std::optional<std::string> prompt = build_prompt(vocabulary, context);
+    const whisper_full_params p = make_params(language, prompt ? &*prompt : nullptr, 0);
+    if (n <= 0 || !audio) {  // whisper-rs rejects an empty slice before the FFI call
+        whisper_free_state(st);
+        return WhisperError{WhisperError::TranscriptionError, "Input sample buffer was empty."};
+    }
+    const int rc = whisper_full_with_state(ctx_, st, p, audio, n);                   // whisper.rs:127-129
+    if (rc != 0) {
+        whisper_free_state(st);
+        return WhisperError{WhisperError::TranscriptionError, "whisper_full_with_state returned " + std::to_string(rc) + ": " + whisper_b200_last_error()};
+    }
+    out = filter_hallucinations(trim(collect_text(st)));                             // whisper.rs:143-144
+    whisper_free_state(st);
+    return WhisperError{};
+}
+
+WhisperError WhisperEngine::transcribe_chunked(const std::vector<std::vector<float>>& chunks, const std::optional<std::string>& language,
+                                               const std::optional<std::string>& vocabulary, std::string& out) const {
+    out.clear();
+    std::vector<std::string> results;
+    std::optional<std::string> last_context;
+    for (const auto& chunk : chunks) {
+        std::string text;
+        WhisperError e = transcribe(chunk.data(), (int)chunk.size(), language, vocabulary, last_context, text);
+        if (e.kind != WhisperError::None) return e;  // abort on the first failing chunk (whisper.rs:182-185)
+        if (!text.empty()) {
+            last_context = text;
+            results.push_back(text);
+        }
+    }
+    for (size_t i = 0; i < results.size(); ++i) {
+        if (i) out += " ";
+        out += results[i];
+    }
+    return WhisperError{};
+}
+
+WhisperError WhisperEngine::transcribe_batch(const std::vector<const float*>& audios, const std::vector<int>& n,
+                                             const std::optional<std::string>& language, const std::optional<std::string>& vocabulary,
+                                             int beam_size, std::vector<std::string>& out) const {
+    out.clear();
+    if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
+    const int cnt = (int)audios.size();
+    if (cnt == 0) return WhisperError{};
+    if (n.size() != audios.size()) return WhisperError{WhisperError::TranscriptionError, "audios / lengths size mismatch"};
+    std::vector<whisper_state*> states(cnt, nullptr);
+    auto free_states = [&]() { for (auto* s : states) whisper_free_state(s); };
+    for (int i = 0; i < cnt; ++i) {
+        if (!audios[i] || n[i] <= 0) { free_states(); return WhisperError{WhisperError::TranscriptionError, "Input sample buffer was empty."}; }
+        states[i] = whisper_init_state(ctx_);
+        if (!states[i]) { free_states(); return WhisperError{WhisperError::TranscriptionError, whisper_b200_last_error()}; }
+    }
+    const std::optional<std::string> prompt = build_prompt(vocabulary, std::nullopt);
+    const whisper_full_params p = make_params(language, prompt ? &*prompt : nullptr, beam_size);
+    std::vector<int> rc(cnt, 0);
+    const int r = whisper_b200_full_batch(ctx_, states.data(), cnt, p, audios.data(), n.data(), rc.data());
+    int bad = r;
+    for (int i = 0; i < cnt && bad == 0; ++i) bad = rc[i];
+    if (bad != 0) {
+        free_states();
+        return WhisperError{WhisperError::TranscriptionError, "whisper_b200_full_batch returned " + std::to_string(bad) + ": " + whisper_b200_last_error()};
+    }
+    out.resize(cnt);
+    for (int i = 0; i < cnt; ++i) out[i] = filter_hallucinations(trim(collect_text(states[i])));
+    free_states();
+    return WhisperError{};
+}
+
+}  // namespace nobs
+
+// ------------------------------------------------------------------------------------------
+// C shims (declared in include/whisper_b200.h) so C / ctypes callers reach the same wrapper
+// ------------------------------------------------------------------------------------------
+struct nobs_engine {
+    nobs::WhisperEngine engine;
+    std::string last_error;
+    std::string text;
+    std::vector<std::string> texts;
+};
+
+extern "C" {
+
+struct nobs_engine* nobs_engine_new(void) { return new nobs_engine(); }
+void nobs_engine_free(struct nobs_engine* e) { delete e; }
+int nobs_engine_load_model(struct nobs_engine* e, const char* path) {
+    const nobs::WhisperError err = e->engine.load_model(path ? path : "");
+    e->last_error = err.to_string();
+    return (int)err.kind;
+}
+void nobs_engine_unload_model(struct nobs_engine* e) { e->engine.unload_model(); }
+int nobs_engine_is_loaded(struct nobs_engine* e) { return e->engine.is_loaded() ? 1 : 0; }
+
+static std::optional<std::string> opt(const char* s) { return s ? std::optional<std::string>(s) : std::nullopt; }
+
+int nobs_engine_transcribe(struct nobs_engine* e, const float* audio, int n, const char* language, const char* vocabulary, const char* context,
+                           const char** out) {
+    const nobs::WhisperError err = e->engine.transcribe(audio, n, opt(language), opt(vocabulary), opt(context), e->text);
+    e->last_error = err.to_string();
+    if (out) *out = e->text.c_str();
+    return (int)err.kind;
+}
+int nobs_engine_transcribe_chunked(struct nobs_engine* e, const float* const* chunks, const int* n, int n_chunks, const char* language,
+                                   const char* vocabulary, const char** out) {
+    std::vector<std::vector<float>> cs;
+    for (int i = 0; i < n_chunks; ++i) cs.emplace_back(chunks[i], chunks[i] + std::max(0, n[i]));
+    const nobs::WhisperError err = e->engine.transcribe_chunked(cs, opt(language), opt(vocabulary), e->text);
+    e->last_error = err.to_string();
+    if (out) *out = e->text.c_str();
+    return (int)err.kind;
+}
+int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audios, const int* n, int n_audios, const char* language,
+                                 const char* vocabulary, int beam_size, const char** texts) {
+    std::vector<const float*> a(audios, audios + n_audios);
+    std::vector<int> ns(n, n + n_audios);
+    const nobs::WhisperError err = e->engine.transcribe_batch(a, ns, opt(language), opt(vocabulary), beam_size, e->texts);
+    e->last_error = err.to_string();
+    if (err.kind == nobs::WhisperError::None && texts)
+        for (int i = 0; i < n_audios; ++i) texts[i] = e->texts[i].c_str();
+    return (int)err.kind;
+}
+const char* nobs_engine_last_error(struct nobs_engine* e) { return e->last_error.c_str(); }
+const char* nobs_filter_hallucinations(const char* text) {
+    static thread_local std::string buf;
+    buf = nobs::filter_hallucinations(text ? text : "");
+    return buf.c_str();
+}
+
+}  // extern "C"

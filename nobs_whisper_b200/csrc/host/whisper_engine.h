@@ -1,0 +1,57 @@
+// C++ host-side mirror of the reference's engine wrapper (reference src-tauri/src/whisper.rs:16-260)
+// written above the C ABI (include/whisper_b200.h).  The reference's host language is Rust; no
+// Rust toolchain exists in this image, so the wrapper logic — prompt assembly, the fixed
+// parameter block, segment concatenation, hallucination filter, chunk chaining — is restated
+// here with the same names, argument meaning and error behaviour.  The equivalent Rust FFI
+// crate source is in rust/ and INTEGRATION.md.
+#pragma once
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../../include/whisper_b200.h"
+
+namespace nobs {
+
+// reference whisper.rs:5-14  enum WhisperError { LoadError(String), TranscriptionError(String), NoModel }
+struct WhisperError {
+    enum Kind { None = 0, LoadError = 1, TranscriptionError = 2, NoModel = 3 } kind = None;
+    std::string message;
+    std::string to_string() const;  // same wording as the reference's #[error(...)] strings
+};
+
+// reference whisper.rs:233-260 (+ phrase list :202-230)
+std::string filter_hallucinations(const std::string& text);
+
+class WhisperEngine {
+public:
+    WhisperEngine() = default;                      // whisper.rs:22-27  new()
+    ~WhisperEngine();
+    WhisperEngine(const WhisperEngine&) = delete;
+    WhisperEngine& operator=(const WhisperEngine&) = delete;
+
+    WhisperError load_model(const std::string& model_path);   // whisper.rs:36-52
+    void unload_model();                                      // whisper.rs:55-59
+    bool is_loaded() const { return ctx_ != nullptr; }         // whisper.rs:62-64
+
+    // whisper.rs:66-148.  nullopt == Rust None.
+    WhisperError transcribe(const float* audio, int n, const std::optional<std::string>& language,
+                            const std::optional<std::string>& vocabulary, const std::optional<std::string>& context, std::string& out) const;
+    // whisper.rs:152-197: sequential, previous non-empty text becomes the next chunk's context
+    WhisperError transcribe_chunked(const std::vector<std::vector<float>>& chunks, const std::optional<std::string>& language,
+                                    const std::optional<std::string>& vocabulary, std::string& out) const;
+    // B200 addition: independent windows decoded together, no context chaining.
+    // beam_size > 0 selects BeamSearch{beam_size, patience:-1}, otherwise Greedy{best_of:1}.
+    WhisperError transcribe_batch(const std::vector<const float*>& audios, const std::vector<int>& n, const std::optional<std::string>& language,
+                                  const std::optional<std::string>& vocabulary, int beam_size, std::vector<std::string>& out) const;
+
+    whisper_context* raw_context() const { return ctx_; }
+
+private:
+    whisper_full_params make_params(const std::optional<std::string>& language, const std::string* initial_prompt, int beam_size) const;
+    static std::optional<std::string> build_prompt(const std::optional<std::string>& vocabulary, const std::optional<std::string>& context);
+    whisper_context* ctx_ = nullptr;
+    std::string model_path_;
+};
+
+}  // namespace nobs

@@ -1,0 +1,880 @@
+// CUDA-core kernels of the hot path (sm_100a): log-mel, fp32 parity-mode GEMM/attention,
+// LayerNorm, decoder row kernels (embedding, KV scatter, KV-cache attention), and the fused
+// logit filter / log-softmax / argmax / sampling / top-k kernel.
+// The tcgen05 (tensor-core) kernels live in gemm_sm100.cu / attention_sm100.cu.
+#include "kernels.cuh"
+
+#include <atomic>
+#include <climits>
+#include <cmath>
+
+namespace nobs {
+
+static std::atomic<long> g_launches{0};
+long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#define NOBS_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+    // ggml GELU: 0.5*x*(1 + tanh(sqrt(2/pi)*x*(1 + 0.044715*x^2)))
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
+}
+
+__device__ __forceinline__ int float_key(float f) {  // order-preserving float -> int
+    int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide reductions (blockDim.x multiple of 32, <= 1024); `red` holds >= 32 elements
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T ident, Op op, T* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = lane < nw ? red[lane] : ident;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;  // every thread holds the result
+}
+struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpAddF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
+
+// ------------------------------------------------------------------------------------------
+// K1: log-mel.  One warp per frame: windowed samples -> 16 x DFT-25 -> 4 radix-2 stages in
+// shared memory -> power -> sparse mel filterbank (double accumulate) -> log10.
+// HBM traffic: each PCM sample is fetched once from DRAM (neighbouring frames re-hit L1/L2),
+// each output value written once.
+// ------------------------------------------------------------------------------------------
+constexpr int kMelWarps = 4;
+
+__global__ void __launch_bounds__(kMelWarps * 32) mel_stft_kernel(MelTables t, const MelJob* __restrict__ jobs, int frames_per_block) {
+    __shared__ float2 s_tw[kNFft];
+    __shared__ float s_hann[kNFft];
+    __shared__ float s_x[kMelWarps][kNFft];
+    __shared__ float2 s_a[kMelWarps][kNFft];
+    __shared__ float2 s_b[kMelWarps][kNFft];
+
+    const MelJob job = jobs[blockIdx.y];
+    const int f_begin = blockIdx.x * frames_per_block;
+    if (f_begin >= job.n_frames) return;
+    for (int i = threadIdx.x; i < kNFft; i += blockDim.x) {
+        s_tw[i] = t.tw[i];
+        s_hann[i] = t.hann[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* x = s_x[warp];
+    float2* A = s_a[warp];
+    float2* B = s_b[warp];
+    const int f_end = min(f_begin + frames_per_block, job.n_frames);
+    float wmax = -INFINITY;
+
+    for (int f = f_begin + warp; f < f_end; f += kMelWarps) {
+        const int base = f * kHop - kNFft / 2;  // sample index of window element 0
+        if (base >= 0 && base + kNFft <= job.n_samples) {
+            const float4* p = reinterpret_cast<const float4*>(job.pcm + base);  // base % 4 == 0, pcm 16B aligned
+            for (int j = lane; j < kNFft / 4; j += 32) {
+                const float4 v = __ldg(p + j);
+                x[4 * j + 0] = v.x * s_hann[4 * j + 0];
+                x[4 * j + 1] = v.y * s_hann[4 * j + 1];
+                x[4 * j + 2] = v.z * s_hann[4 * j + 2];
+                x[4 * j + 3] = v.w * s_hann[4 * j + 3];
+            }
+        } else {
+            for (int j = lane; j < kNFft; j += 32) {
+                const int s = base + j;
+                float v = 0.0f;
+                if (s < 0) { if (-s < job.n_samples) v = job.pcm[-s]; }   // reflect pad on the left edge
+                else if (s < job.n_samples) v = job.pcm[s];                // zeros past the right edge
+                x[j] = v * s_hann[j];
+            }
+        }
+        __syncwarp();
+        // 16 DFTs of length 25 over the residues n mod 16
+        for (int o = lane; o < kNFft; o += 32) {
+            const int r = o / 25, k = o - r * 25;
+            float re = 0.0f, im = 0.0f;
+#pragma unroll 5
+            for (int m = 0; m < 25; ++m) {
+                const float xv = x[16 * m + r];
+                const float2 w = s_tw[16 * ((m * k) % 25)];
+                re += xv * w.x;
+                im -= xv * w.y;
+            }
+            A[o] = make_float2(re, im);
+        }
+        __syncwarp();
+        // radix-2 combines: (R,L) = (16,25) -> (8,50) -> (4,100) -> (2,200) -> (1,400)
+        float2* in = A;
+        float2* out = B;
+#pragma unroll
+        for (int stage = 0; stage < 4; ++stage) {
+            const int L = 25 << stage, halfR = 8 >> stage, step = kNFft / (2 * L);
+            for (int o = lane; o < kNFft / 2; o += 32) {
+                const int r = o / L, k = o - r * L;
+                const float2 e = in[r * L + k];
+                const float2 od = in[(r + halfR) * L + k];
+                const float2 w = s_tw[k * step];
+                const float tr = w.x * od.x + w.y * od.y;
+                const float ti = w.x * od.y - w.y * od.x;
+                out[r * 2 * L + k] = make_float2(e.x + tr, e.y + ti);
+                out[r * 2 * L + k + L] = make_float2(e.x - tr, e.y - ti);
+            }
+            __syncwarp();
+            float2* tmp = in; in = out; out = tmp;
+        }
+        // power spectrum of bins 0..200 (x is free again)
+        for (int k = lane; k < kNFreq; k += 32) {
+            const float2 v = in[k];
+            x[k] = v.x * v.x + v.y * v.y;
+        }
+        __syncwarp();
+        for (int m = lane; m < t.n_mel; m += 32) {
+            const int2 rg = t.ranges[m];
+            const float* fl = t.filters + (size_t)m * kNFreq;
+            double sum = 0.0;
+            for (int k = rg.x; k < rg.y; ++k) sum += (double)__fmul_rn(x[k], __ldg(fl + k));
+            const float v = (float)log10(fmax(sum, 1e-10));
+            job.raw[(size_t)f * t.n_mel + m] = v;
+            wmax = fmaxf(wmax, v);
+        }
+        __syncwarp();
+    }
+    wmax = warp_max(wmax);
+    if (lane == 0 && wmax > -INFINITY) atomicMax(job.max_key, float_key(wmax));
+}
+
+void launch_mel_stft(const MelTables& t, const MelJob* jobs_dev, int n_jobs, int max_frames, cudaStream_t s) {
+    if (n_jobs <= 0 || max_frames <= 0) return;
+    const int frames_per_block = 32;
+    dim3 grid((max_frames + frames_per_block - 1) / frames_per_block, n_jobs);
+    mel_stft_kernel<<<grid, kMelWarps * 32, 0, s>>>(t, jobs_dev, frames_per_block);
+    NOBS_COUNT_LAUNCH();
+}
+
+// normalisation shared by pack/export: global max over all frames (frames past n_frames are
+// exactly -10), clamp to max-8, (x+4)/4 — in double like the reference path.
+__device__ __forceinline__ float mel_normalise(float raw, double mmax) {
+    double v = raw;
+    if (v < mmax) v = (double)(float)mmax;
+    return (float)((v + 4.0) / 4.0);
+}
+__device__ __forceinline__ double mel_clamp_floor(const int* max_key, int n_frames, int n_len) {
+    float gmax = key_float(*max_key);
+    if (n_frames < n_len) gmax = fmaxf(gmax, -10.0f);
+    return (double)gmax - 8.0;
+}
+
+template <typename T>
+__global__ void pack_mel_kernel(const PackJob* __restrict__ jobs, int n_mel, T* __restrict__ dst) {
+    const PackJob j = jobs[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kWinRowsIn * n_mel) return;
+    const int t = idx / n_mel, c = idx - t * n_mel;
+    float v = 0.0f;
+    const int frame = j.seek + t;
+    if (t < 3000 && frame < j.n_len) {
+        const double mmax = mel_clamp_floor(j.max_key, j.n_frames, j.n_len);
+        const float raw = frame < j.n_frames ? j.raw[(size_t)frame * n_mel + c] : -10.0f;
+        v = mel_normalise(raw, mmax);
+    }
+    dst[((size_t)blockIdx.y * kWinRowsIn + 1 + t) * n_mel + c] = from_f32<T>(v);
+}
+
+template <typename T>
+void launch_pack_mel(const PackJob* jobs_dev, int n_win, int n_mel, T* dst, cudaStream_t s) {
+    if (n_win <= 0) return;
+    dim3 grid((kWinRowsIn * n_mel + 255) / 256, n_win);
+    pack_mel_kernel<T><<<grid, 256, 0, s>>>(jobs_dev, n_mel, dst);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_pack_mel<float>(const PackJob*, int, int, float*, cudaStream_t);
+template void launch_pack_mel<bf16>(const PackJob*, int, int, bf16*, cudaStream_t);
+
+__global__ void export_mel_kernel(const float* __restrict__ raw, const int* __restrict__ max_key, int n_frames, int n_len, int n_mel,
+                                  float* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_len * n_mel) return;
+    const int c = (int)(idx / n_len), i = (int)(idx - (size_t)c * n_len);
+    const double mmax = mel_clamp_floor(max_key, n_frames, n_len);
+    const float r = i < n_frames ? raw[(size_t)i * n_mel + c] : -10.0f;
+    out[idx] = mel_normalise(r, mmax);
+}
+void launch_export_mel(const float* raw, const int* max_key, int n_frames, int n_len, int n_mel, float* out, cudaStream_t s) {
+    const size_t n = (size_t)n_len * n_mel;
+    export_mel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(raw, max_key, n_frames, n_len, n_mel, out);
+    NOBS_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 GEMM (parity mode): C = epi(A * W^T), 128x128x16 tiles, 8x8 per thread.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const Epilogue& e) {
+    float v = acc;
+    if (e.bias) v += __ldg(e.bias + n);
+    if (e.act == 1) v = gelu_tanh(v);
+    if (e.res) {
+        const int rm = e.res_mod > 0 ? m % e.res_mod : m;
+        v += e.res[(size_t)rm * e.res_ld + n];
+    }
+    if (e.win_rows > 0 && (m % e.win_rows) >= e.valid_rows) v = 0.0f;
+    return v;
+}
+
+constexpr int GB_M = 128, GB_N = 128, GB_K = 16;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                       float* C, int ldc, int M, int N, int K, Epilogue e) {
+    __shared__ __align__(16) float As[GB_K][GB_M + 4];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < K; k0 += GB_K) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int idx = tid + p * 256;
+            const int row = idx >> 2, kq = (idx & 3) * 4;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (m0 + row < M) va = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + kq);
+            if (n0 + row < N) vb = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * ldw + k0 + kq));
+            As[kq + 0][row] = va.x; As[kq + 1][row] = va.y; As[kq + 2][row] = va.z; As[kq + 3][row] = va.w;
+            Bs[kq + 0][row] = vb.x; Bs[kq + 1][row] = vb.y; Bs[kq + 2][row] = vb.z; Bs[kq + 3][row] = vb.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GB_K; ++k) {
+            float a[8], b[8];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + tx * 8 + j;
+            if (n < N) C[(size_t)m * ldc + n] = apply_epilogue(acc[i][j], m, n, e);
+        }
+    }
+}
+
+void launch_gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, const Epilogue& e,
+                     cudaStream_t s) {
+    if (M <= 0 || N <= 0) return;
+    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
+    gemm_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, e);
+    NOBS_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5), one warp per row, fp32 statistics
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ idx,
+                                                        const float* __restrict__ g, const float* __restrict__ b, TO* __restrict__ y,
+                                                        int ldy, int rows, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (size_t)(idx ? idx[row] : row) * ldx;
+    float sum = 0.0f;
+    for (int i = lane; i < d; i += 32) sum += xr[i];
+    const float mean = warp_sum(sum) / d;
+    float var = 0.0f;
+    for (int i = lane; i < d; i += 32) { const float t = xr[i] - mean; var += t * t; }
+    var = warp_sum(var) / d;
+    const float inv = rsqrtf(var + 1e-5f);
+    TO* yr = y + (size_t)row * ldy;
+    for (int i = lane; i < d; i += 32) yr[i] = from_f32<TO>((xr[i] - mean) * inv * __ldg(g + i) + __ldg(b + i));
+}
+
+template <typename TO>
+void launch_layernorm(const float* x, int ldx, const float* g, const float* b, TO* y, int ldy, int rows, int d, cudaStream_t s) {
+    if (rows <= 0) return;
+    layernorm_kernel<TO><<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, nullptr, g, b, y, ldy, rows, d);
+    NOBS_COUNT_LAUNCH();
+}
+template <typename TO>
+void launch_layernorm_gather(const float* x, int ldx, const int* idx, const float* g, const float* b, TO* y, int ldy, int rows, int d,
+                             cudaStream_t s) {
+    if (rows <= 0) return;
+    layernorm_kernel<TO><<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, idx, g, b, y, ldy, rows, d);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, int, int, cudaStream_t);
+template void launch_layernorm<bf16>(const float*, int, const float*, const float*, bf16*, int, int, int, cudaStream_t);
+template void launch_layernorm_gather<float>(const float*, int, const int*, const float*, const float*, float*, int, int, int, cudaStream_t);
+template void launch_layernorm_gather<bf16>(const float*, int, const int*, const float*, const float*, bf16*, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// Encoder self-attention, fp32 parity mode: flash-style, 64 queries x 64 keys per step,
+// 256 threads, each owning a 4x4 block of S and of O.
+// ------------------------------------------------------------------------------------------
+constexpr int EA_BQ = 64, EA_BK = 64, EA_DH = 64;
+
+__global__ void __launch_bounds__(256) enc_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int d, int n_valid) {
+    extern __shared__ __align__(16) float ea_smem[];
+    float (*Qs)[EA_DH + 4] = reinterpret_cast<float (*)[EA_DH + 4]>(ea_smem);                              // [64][68]
+    float (*Kt)[EA_BK + 4] = reinterpret_cast<float (*)[EA_BK + 4]>(ea_smem + EA_BQ * (EA_DH + 4));          // [dh][64+4]
+    float (*Vs)[EA_DH + 4] = reinterpret_cast<float (*)[EA_DH + 4]>(ea_smem + 2 * EA_BQ * (EA_DH + 4));      // [64][68]
+    float (*Ps)[EA_BK + 4] = reinterpret_cast<float (*)[EA_BK + 4]>(ea_smem + 3 * EA_BQ * (EA_DH + 4));      // [64][68]
+
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
+    const size_t ld = (size_t)3 * d;
+    const float* base = qkv + (size_t)w * kWinRows * ld;
+    const float* Qg = base + (size_t)qt * EA_BQ * ld + h * EA_DH;
+    const float* Kg = base + d + h * EA_DH;
+    const float* Vg = base + 2 * d + h * EA_DH;
+
+    for (int i = tid; i < EA_BQ * EA_DH / 4; i += 256) {
+        const int r = i >> 4, c = (i & 15) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(Qg + (size_t)r * ld + c);
+        *reinterpret_cast<float4*>(&Qs[r][c]) = v;
+    }
+    float m_i[4], l_i[4], O[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_i[i] = -INFINITY;
+        l_i[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) O[i][j] = 0.0f;
+    }
+    const int n_tiles = (n_valid + EA_BK - 1) / EA_BK;
+    for (int kt = 0; kt < n_tiles; ++kt) {
+        __syncthreads();  // previous tile fully consumed (also orders the Q store on the first pass)
+        for (int i = tid; i < EA_BK * EA_DH / 4; i += 256) {
+            const int r = i >> 4, c = (i & 15) * 4;
+            const int key = kt * EA_BK + r;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (key < n_valid) {
+                kv = *reinterpret_cast<const float4*>(Kg + (size_t)key * ld + c);
+                vv = *reinterpret_cast<const float4*>(Vg + (size_t)key * ld + c);
+            }
+            Kt[c + 0][r] = kv.x; Kt[c + 1][r] = kv.y; Kt[c + 2][r] = kv.z; Kt[c + 3][r] = kv.w;
+            *reinterpret_cast<float4*>(&Vs[r][c]) = vv;
+        }
+        __syncthreads();
+        float S[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[i][j] = 0.0f;
+#pragma unroll 8
+        for (int e = 0; e < EA_DH; ++e) {
+            const float4 kk = *reinterpret_cast<const float4*>(&Kt[e][tx * 4]);
+            float q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = Qs[ty * 4 + i][e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                S[i][0] = fmaf(q[i], kk.x, S[i][0]);
+                S[i][1] = fmaf(q[i], kk.y, S[i][1]);
+                S[i][2] = fmaf(q[i], kk.z, S[i][2]);
+                S[i][3] = fmaf(q[i], kk.w, S[i][3]);
+            }
+        }
+        // scale, mask padded keys, online softmax
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float rmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = kt * EA_BK + tx * 4 + j;
+                S[i][j] = key < n_valid ? S[i][j] * 0.125f : -INFINITY;
+                rmax = fmaxf(rmax, S[i][j]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+            const float m_new = fmaxf(m_i[i], rmax);
+            const float corr = __expf(m_i[i] - m_new);  // 0 on the first tile (m_i = -inf)
+            float rsum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                S[i][j] = expf(S[i][j] - m_new);
+                rsum += S[i][j];
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+            l_i[i] = l_i[i] * corr + rsum;
+            m_i[i] = m_new;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) O[i][j] *= corr;
+            *reinterpret_cast<float4*>(&Ps[ty * 4 + i][tx * 4]) = make_float4(S[i][0], S[i][1], S[i][2], S[i][3]);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < EA_BK; ++j) {
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float p = Ps[ty * 4 + i][j];
+                O[i][0] = fmaf(p, vv.x, O[i][0]);
+                O[i][1] = fmaf(p, vv.y, O[i][1]);
+                O[i][2] = fmaf(p, vv.z, O[i][2]);
+                O[i][3] = fmaf(p, vv.w, O[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float inv = 1.0f / l_i[i];
+        const size_t row = (size_t)w * kWinRows + qt * EA_BQ + ty * 4 + i;
+        *reinterpret_cast<float4*>(out + row * d + h * EA_DH + tx * 4) = make_float4(O[i][0] * inv, O[i][1] * inv, O[i][2] * inv, O[i][3] * inv);
+    }
+}
+
+void launch_enc_attention_f32(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s) {
+    if (n_win <= 0) return;
+    const int smem = 4 * EA_BQ * (EA_DH + 4) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(enc_attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    dim3 grid(kWinRows / EA_BQ, n_head, n_win);
+    enc_attention_f32_kernel<<<grid, 256, smem, s>>>(qkv, out, d, 1500);
+    NOBS_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoder row kernels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_kernel(const RowDesc* __restrict__ rows, int n_rows, const T* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                             float* __restrict__ x, int d) {
+    const int r = blockIdx.x;
+    const RowDesc rd = rows[r];
+    const T* te = tok_emb + (size_t)rd.token * d;
+    const float* pe = pos_emb + (size_t)rd.pos * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)r * d + i] = to_f32(te[i]) + pe[i];
+}
+template <typename T>
+void launch_embed(const RowDesc* rows, int n_rows, const T* tok_emb, const float* pos_emb, float* x, int d, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    embed_kernel<T><<<n_rows, 128, 0, s>>>(rows, n_rows, tok_emb, pos_emb, x, d);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_embed<float>(const RowDesc*, int, const float*, const float*, float*, int, cudaStream_t);
+template void launch_embed<bf16>(const RowDesc*, int, const bf16*, const float*, float*, int, cudaStream_t);
+
+template <typename T>
+__global__ void scatter_kv_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
+                                  size_t slot_stride, int d) {
+    const int r = blockIdx.x;
+    const RowDesc rd = rows[r];
+    const T* src = qkv + (size_t)r * 3 * d;
+    const size_t dst = (size_t)rd.kv_slot * slot_stride + (size_t)rd.pos * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        kc[dst + i] = src[d + i];
+        vc[dst + i] = src[2 * d + i];
+    }
+}
+template <typename T>
+void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kcache, T* vcache, size_t slot_stride, int d, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    scatter_kv_kernel<T><<<n_rows, 128, 0, s>>>(rows, qkv, kcache, vcache, slot_stride, d);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_scatter_kv<float>(const RowDesc*, int, const float*, float*, float*, size_t, int, cudaStream_t);
+template void launch_scatter_kv<bf16>(const RowDesc*, int, const bf16*, bf16*, bf16*, size_t, int, cudaStream_t);
+
+// dot of a 64-wide fp32 query (shared memory) with one K row
+__device__ __forceinline__ float dot64(const float* __restrict__ q, const float* __restrict__ k) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(k) + i);
+        acc = fmaf(q[4 * i + 0], v.x, acc);
+        acc = fmaf(q[4 * i + 1], v.y, acc);
+        acc = fmaf(q[4 * i + 2], v.z, acc);
+        acc = fmaf(q[4 * i + 3], v.w, acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ float dot64(const float* __restrict__ q, const bf16* __restrict__ k) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(k) + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            acc = fmaf(q[8 * i + 2 * j + 0], f.x, acc);
+            acc = fmaf(q[8 * i + 2 * j + 1], f.y, acc);
+        }
+    }
+    return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dec_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+                                                            const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
+                                                            int cross, size_t slot_stride, size_t key_stride, int n_keys) {
+    __shared__ __align__(16) float qs[64];
+    __shared__ float sc[kWinRows];
+    __shared__ float red[32];
+    __shared__ float part[4][64];
+    const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const RowDesc rd = rows[r];
+    const int nk = cross ? n_keys : rd.pos + 1;
+    const size_t base = (size_t)(cross ? rd.audio_slot : rd.kv_slot) * slot_stride + (size_t)h * 64;
+    const T* K = kc + base;
+    const T* V = vc + base;
+    if (tid < 64) qs[tid] = to_f32(q[(size_t)r * ldq + h * 64 + tid]);
+    __syncthreads();
+    float lmax = -INFINITY;
+    for (int j = tid; j < nk; j += 256) {
+        const float s = dot64(qs, K + (size_t)j * key_stride) * 0.125f;
+        sc[j] = s;
+        lmax = fmaxf(lmax, s);
+    }
+    const float mx = block_reduce(lmax, -INFINITY, OpMax(), red);
+    float lsum = 0.0f;
+    for (int j = tid; j < nk; j += 256) {
+        const float p = expf(sc[j] - mx);
+        sc[j] = p;
+        lsum += p;
+    }
+    const float total = block_reduce(lsum, 0.0f, OpAddF(), red);  // includes the barrier that publishes sc[]
+    const float inv = 1.0f / total;
+    const int g = tid >> 6, e = tid & 63;
+    float acc = 0.0f;
+    for (int j = g; j < nk; j += 4) acc = fmaf(sc[j], to_f32(V[(size_t)j * key_stride + e]), acc);
+    part[g][e] = acc;
+    __syncthreads();
+    if (tid < 64) {
+        const float o = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv;
+        out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o);
+    }
+}
+template <typename T>
+void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
+                          int cross, size_t slot_stride, size_t key_stride, int n_keys, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    dim3 grid(n_rows, n_head);
+    dec_attention_kernel<T><<<grid, 256, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, key_stride, n_keys);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_dec_attention<float>(const RowDesc*, int, const float*, int, const float*, const float*, float*, int, int, int, size_t, size_t,
+                                          int, cudaStream_t);
+template void launch_dec_attention<bf16>(const RowDesc*, int, const bf16*, int, const bf16*, const bf16*, bf16*, int, int, int, size_t, size_t, int,
+                                         cudaStream_t);
+
+// beam search: copy the first n_pos positions of every (layer, K|V) block of one self-KV slot to another
+template <typename T>
+__global__ void kv_copy_kernel(const KvCopy* __restrict__ pairs, T* __restrict__ pool, size_t slot_stride, size_t block_stride, int d) {
+    const KvCopy p = pairs[blockIdx.x];
+    const size_t n = (size_t)p.n_pos * d;
+    const T* src = pool + (size_t)p.src * slot_stride + (size_t)blockIdx.y * block_stride;
+    T* dst = pool + (size_t)p.dst * slot_stride + (size_t)blockIdx.y * block_stride;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+template <typename T>
+void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_blocks, size_t block_stride, int d, cudaStream_t s) {
+    if (n_pairs <= 0) return;
+    dim3 grid(n_pairs, n_blocks);
+    kv_copy_kernel<T><<<grid, 256, 0, s>>>(pairs, pool, slot_stride, block_stride, d);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_kv_copy<float>(const KvCopy*, int, float*, size_t, int, size_t, int, cudaStream_t);
+template void launch_kv_copy<bf16>(const KvCopy*, int, bf16*, size_t, int, size_t, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// K6: logit filter + log-softmax + timestamp rule + argmax / sample / top-k, one block per row.
+// Restates the reference path's per-step logit processing.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool token_suppressed(int i, const SampleParams& p, const VocabIds& v) {
+    if (p.suppress_blank && p.is_initial && (i == v.eot || i == v.blank)) return true;
+    if (i == v.not_ || i == v.sot || i == v.nosp || i == v.solm || i == v.translate || i == v.transcribe || i == v.prev) return true;
+    if (i > v.sot && i <= v.sot + v.n_lang) return true;
+    if (i >= v.beg) {
+        if (p.no_timestamps) return true;
+        if (p.last_was_ts && p.penult_was_ts) return true;
+        if (p.is_initial && i >= p.ts_initial_limit) return true;
+        if (p.has_ts && i < p.ts_min) return true;
+    } else if (p.last_was_ts && !p.penult_was_ts && i < v.eot) {
+        return true;
+    }
+    return false;
+}
+
+constexpr int PL_THREADS = 1024;
+
+__global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float* __restrict__ logits, int ld,
+                                                                    const SampleParams* __restrict__ params, SampleResult* __restrict__ results,
+                                                                    VocabIds v, float* __restrict__ logprobs_out, float* __restrict__ probs_out) {
+    __shared__ float red_f[32];
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ double scan_d[32];
+    __shared__ int s_pick;
+    __shared__ int s_chosen[kMaxTopK];
+
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const SampleParams p = params[row];
+    const float* lg = logits + (size_t)row * ld;
+    const int n = v.n_vocab;
+    const bool scaled = p.temperature > 0.0f;
+
+    // pass A: maxima
+    float lmax = -INFINITY, rawmax = -INFINITY;
+    for (int i = tid; i < n; i += PL_THREADS) {
+        const float raw = lg[i];
+        rawmax = fmaxf(rawmax, raw);
+        if (!token_suppressed(i, p, v)) lmax = fmaxf(lmax, scaled ? __fdiv_rn(raw, p.temperature) : raw);
+    }
+    lmax = block_reduce(lmax, -INFINITY, OpMax(), red_f);
+    rawmax = block_reduce(rawmax, -INFINITY, OpMax(), red_f);
+    // pass B: sums
+    float lsum = 0.0f, rawsum = 0.0f;
+    for (int i = tid; i < n; i += PL_THREADS) {
+        const float raw = lg[i];
+        if (p.want_nosp) rawsum += expf(raw - rawmax);
+        if (!token_suppressed(i, p, v)) lsum += expf((scaled ? __fdiv_rn(raw, p.temperature) : raw) - lmax);
+    }
+    lsum = block_reduce(lsum, 0.0f, OpAddF(), red_f);
+    rawsum = block_reduce(rawsum, 0.0f, OpAddF(), red_f);
+    const float logsumexp = logf(lsum) + lmax;
+    auto logprob_of = [&](int i) -> float {
+        if (token_suppressed(i, p, v)) return -INFINITY;
+        const float l = scaled ? __fdiv_rn(lg[i], p.temperature) : lg[i];
+        return l - logsumexp;
+    };
+    // pass C: timestamp logsumexp vs best text token
+    float ts_max = -INFINITY, text_max = -INFINITY;
+    for (int i = tid; i < n; i += PL_THREADS) {
+        const float lp = logprob_of(i);
+        if (i >= v.beg) ts_max = fmaxf(ts_max, lp); else text_max = fmaxf(text_max, lp);
+    }
+    ts_max = block_reduce(ts_max, -INFINITY, OpMax(), red_f);
+    text_max = block_reduce(text_max, -INFINITY, OpMax(), red_f);
+    float ts_sum = 0.0f;
+    for (int i = v.beg + tid; i < n; i += PL_THREADS) {
+        const float lp = logprob_of(i);
+        if (lp > -INFINITY) ts_sum += expf(lp - ts_max);
+    }
+    ts_sum = block_reduce(ts_sum, 0.0f, OpAddF(), red_f);
+    const float ts_logprob = ts_sum > 0.0f ? logf(ts_sum) + ts_max : -INFINITY;
+    const bool text_off = ts_logprob > text_max;
+
+    auto final_logprob = [&](int i) -> float {
+        if (text_off && i < v.beg) return -INFINITY;
+        return logprob_of(i);
+    };
+
+    // pass D: probabilities, argmax (first maximum wins), timestamp statistics
+    float best_p = 0.0f; int best_i = INT_MAX;
+    float tsb_p = 0.0f; int tsb_i = INT_MAX;
+    double sum_ts = 0.0, sum_all = 0.0;
+    for (int i = tid; i < n; i += PL_THREADS) {
+        const float lp = final_logprob(i);
+        const float pr = lp > -INFINITY ? expf(lp) : 0.0f;
+        if (logprobs_out) logprobs_out[(size_t)row * n + i] = lp;
+        if (probs_out) probs_out[(size_t)row * n + i] = pr;
+        if (pr > best_p) { best_p = pr; best_i = i; }          // strided ascending: keeps this thread's first max
+        if (i >= v.beg) {
+            sum_ts += pr;
+            if (pr > tsb_p) { tsb_p = pr; tsb_i = i; }
+        }
+        sum_all += pr;
+    }
+    const float gbest_p = block_reduce(best_p, 0.0f, OpMax(), red_f);
+    int cand = (best_p == gbest_p && best_i != INT_MAX) ? best_i : INT_MAX;
+    const int gbest_i = block_reduce(cand, INT_MAX, OpMinI(), red_i);
+    const float gts_p = block_reduce(tsb_p, 0.0f, OpMax(), red_f);
+    cand = (tsb_p == gts_p && tsb_i != INT_MAX) ? tsb_i : INT_MAX;
+    const int gts_i = block_reduce(cand, INT_MAX, OpMinI(), red_i);
+    sum_ts = block_reduce(sum_ts, 0.0, OpAddD(), red_d);
+
+    int pick = gbest_i == INT_MAX ? 0 : gbest_i;
+    if (p.mode == 1) {
+        // inverse-CDF sampling identical in structure to std::discrete_distribution:
+        // q_i = p_i / sum, cp = inclusive prefix sums of q, pick = first i with cp[i] >= u.
+        const int chunk = (n + PL_THREADS - 1) / PL_THREADS;
+        const int i0 = tid * chunk, i1 = min(n, i0 + chunk);
+        double tot = 0.0;
+        for (int i = i0; i < i1; ++i) { const float lp = final_logprob(i); tot += lp > -INFINITY ? (double)expf(lp) : 0.0; }
+        const double total = block_reduce(tot, 0.0, OpAddD(), red_d);
+        double local = 0.0;
+        for (int i = i0; i < i1; ++i) { const float lp = final_logprob(i); local += (lp > -INFINITY ? (double)expf(lp) : 0.0) / total; }
+        // exclusive scan of `local` over threads
+        const int lane = tid & 31, warp = tid >> 5;
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) scan_d[warp] = incl;
+        if (tid == 0) s_pick = n - 1;  // cp.back() is forced to 1.0 by the reference distribution
+        __syncthreads();
+        double woff = 0.0;
+        for (int w = 0; w < warp; ++w) woff += scan_d[w];
+        double cp = woff + incl - local;
+        int found = INT_MAX;
+        for (int i = i0; i < i1; ++i) {
+            const float lp = final_logprob(i);
+            cp += (lp > -INFINITY ? (double)expf(lp) : 0.0) / total;
+            if (cp >= p.u) { found = i; break; }
+        }
+        if (found != INT_MAX) atomicMin(&s_pick, found);
+        __syncthreads();
+        pick = s_pick;
+    }
+
+    int n_topk = 0;
+    if (p.mode == 2) {
+        // k rounds of block arg-max over log-probabilities, ties -> lower id
+        const int k = min(p.k, kMaxTopK);
+        for (int round = 0; round < k; ++round) {
+            float bl = -INFINITY; int bi = INT_MAX;
+            for (int i = tid; i < n; i += PL_THREADS) {
+                bool taken = false;
+                for (int c = 0; c < round; ++c) taken |= (s_chosen[c] == i);
+                if (taken) continue;
+                const float lp = final_logprob(i);
+                if (lp > bl) { bl = lp; bi = i; }
+            }
+            const float gl = block_reduce(bl, -INFINITY, OpMax(), red_f);
+            const int c2 = (bl == gl && bi != INT_MAX && gl > -INFINITY) ? bi : INT_MAX;
+            const int gi = block_reduce(c2, INT_MAX, OpMinI(), red_i);
+            if (gi == INT_MAX) break;  // uniform across the block
+            if (tid == 0) s_chosen[round] = gi;
+            __syncthreads();
+            n_topk = round + 1;
+        }
+    }
+
+    if (tid == 0) {
+        SampleResult r;
+        r.id = pick;
+        const float lp = final_logprob(pick);
+        r.plog = lp;
+        r.p = lp > -INFINITY ? expf(lp) : 0.0f;
+        r.tid = gts_i == INT_MAX ? -1 : gts_i;  // -1: no timestamp has probability > 0 (host picks the default)
+        r.pt = (float)((double)gts_p / (sum_ts + 1e-10));
+        r.ptsum = (float)sum_ts;
+        if (pick >= v.beg) { r.tid = pick; r.pt = r.p; }
+        r.no_speech_prob = p.want_nosp ? expf(lg[v.nosp] - (logf(rawsum) + rawmax)) : 0.0f;
+        r.n_topk = n_topk;
+        for (int c = 0; c < kMaxTopK; ++c) {
+            if (c < n_topk) {
+                const int id = s_chosen[c];
+                const float l2 = final_logprob(id);
+                r.topk_id[c] = id; r.topk_plog[c] = l2; r.topk_p[c] = expf(l2);
+            } else { r.topk_id[c] = -1; r.topk_plog[c] = -INFINITY; r.topk_p[c] = 0.0f; }
+        }
+        results[row] = r;
+    }
+}
+
+void launch_process_logits(const float* logits, int ld, const SampleParams* params, SampleResult* results, int n_rows, const VocabIds& v,
+                           float* logprobs_out, float* probs_out, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    process_logits_kernel<<<n_rows, PL_THREADS, 0, s>>>(logits, ld, params, results, v, logprobs_out, probs_out);
+    NOBS_COUNT_LAUNCH();
+}
+
+__global__ void lang_probs_kernel(const float* __restrict__ logits, VocabIds v, float* __restrict__ probs_out, int* __restrict__ best) {
+    __shared__ float red_f[32];
+    __shared__ int red_i[32];
+    const int tid = threadIdx.x;
+    const float l = tid < v.n_lang ? logits[v.sot + 1 + tid] : -INFINITY;
+    const float mx = block_reduce(l, -INFINITY, OpMax(), red_f);
+    const float e = tid < v.n_lang ? expf(l - mx) : 0.0f;
+    const float sum = block_reduce(e, 0.0f, OpAddF(), red_f);
+    if (tid < v.n_lang && probs_out) probs_out[tid] = e / sum;
+    const int cand = (tid < v.n_lang && l == mx) ? tid : INT_MAX;
+    const int b = block_reduce(cand, INT_MAX, OpMinI(), red_i);
+    if (tid == 0) *best = b;
+}
+void launch_lang_probs(const float* logits, const VocabIds& v, float* probs_out, int* best, cudaStream_t s) {
+    lang_probs_kernel<<<1, 128, 0, s>>>(logits, v, probs_out, best);
+    NOBS_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = from_f32<TO>(to_f32(in[i]));
+}
+template <typename TI, typename TO>
+void launch_convert(const TI* in, TO* out, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    convert_kernel<TI, TO><<<blocks, 256, 0, s>>>(in, out, n);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_convert<float, bf16>(const float*, bf16*, size_t, cudaStream_t);
+template void launch_convert<bf16, float>(const bf16*, float*, size_t, cudaStream_t);
+template void launch_convert<float, float>(const float*, float*, size_t, cudaStream_t);
+
+template <typename TI, typename TO>
+__global__ void convert_2d_kernel(const TI* __restrict__ in, size_t ld_in, TO* __restrict__ out, size_t ld_out, int rows, int cols) {
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+        out[(size_t)r * ld_out + c] = from_f32<TO>(to_f32(in[(size_t)r * ld_in + c]));
+}
+template <typename TI, typename TO>
+void launch_convert_2d(const TI* in, size_t ld_in, TO* out, size_t ld_out, int rows, int cols, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((cols + 255) / 256, rows);
+    convert_2d_kernel<TI, TO><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, rows, cols);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_convert_2d<float, float>(const float*, size_t, float*, size_t, int, int, cudaStream_t);
+template void launch_convert_2d<bf16, float>(const bf16*, size_t, float*, size_t, int, int, cudaStream_t);
+
+}  // namespace nobs

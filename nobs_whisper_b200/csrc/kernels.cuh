@@ -1,0 +1,140 @@
+// Device kernels of the B200 Whisper hot path and their launchers.
+// Stage map: K1 log-mel (a4), K2 conv stem + K3 encoder layers (a7),
+// K4 cross-KV (a8), K5 decoder rows (a9), K6 logit filter / log-softmax / sampling (a10).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace nobs {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kWinRowsIn = 3072;   // padded mel frames per window (3000 valid)
+constexpr int kWinRows = 1536;     // padded encoder positions per window (1500 valid)
+constexpr int kNFft = 400;
+constexpr int kHop = 160;
+constexpr int kNFreq = 201;
+constexpr int kMaxTopK = 8;
+
+// ---------------------------------------------------------------- K1 log-mel
+struct MelTables {           // device pointers, built once per context
+    const float* hann;       // [400]
+    const float2* tw;        // [400] (cos, sin)(2*pi*i/400)
+    const float* filters;    // [n_mel][201]
+    const int2* ranges;      // [n_mel] (first non-zero k, one past last)
+    int n_mel;
+};
+struct MelJob {              // one audio
+    const float* pcm;        // device, n_samples floats
+    int n_samples;
+    int n_frames;            // frames that overlap samples; later frames are exactly log10(1e-10)
+    float* raw;              // [n_frames][n_mel] log10 mel, time-major
+    int* max_key;            // ordered-int key of the running max (init INT_MIN)
+};
+void launch_mel_stft(const MelTables& t, const MelJob* jobs_dev, int n_jobs, int max_frames, cudaStream_t s);
+
+struct PackJob {             // one window to encode
+    const float* raw;        // job raw mel
+    const int* max_key;
+    int n_frames;            // computed frames
+    int n_len;               // total frames of the audio (mel.n_len)
+    int seek;                // first frame of the window
+};
+// dst: [(n_win * kWinRowsIn + 2)][n_mel]; writes rows 1 + w*kWinRowsIn + t
+template <typename T>
+void launch_pack_mel(const PackJob* jobs_dev, int n_win, int n_mel, T* dst, cudaStream_t s);
+// normalised mel in upstream layout [n_mel][n_len] (inspection / parity hook)
+void launch_export_mel(const float* raw, const int* max_key, int n_frames, int n_len, int n_mel, float* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- GEMM epilogue description
+struct Epilogue {
+    const float* bias = nullptr;  // [N]
+    int act = 0;                  // 0 none, 1 GELU (tanh form, as ggml)
+    const float* res = nullptr;   // fp32 residual, row stride res_ld; row index = m % res_mod (res_mod 0: m)
+    int res_ld = 0;
+    int res_mod = 0;
+    int win_rows = 0;             // if > 0: rows with (m % win_rows) >= valid_rows are written as 0
+    int valid_rows = 0;
+};
+
+// C[M,N] = epi(A[M,K] * W[N,K]^T), all fp32, K-contiguous operands (fp32 parity mode)
+void launch_gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, const Epilogue& e,
+                     cudaStream_t s);
+
+// ---------------------------------------------------------------- LayerNorm
+template <typename TO>
+void launch_layernorm(const float* x, int ldx, const float* g, const float* b, TO* y, int ldy, int rows, int d, cudaStream_t s);
+// gathered rows: y[i] = LN(x[idx[i]])
+template <typename TO>
+void launch_layernorm_gather(const float* x, int ldx, const int* idx, const float* g, const float* b, TO* y, int ldy, int rows, int d,
+                             cudaStream_t s);
+
+// ---------------------------------------------------------------- encoder attention (non-causal, 1500 keys)
+// qkv: [n_win*kWinRows][3*d] (q | k | v), out: [n_win*kWinRows][d]
+void launch_enc_attention_f32(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s);
+
+// ---------------------------------------------------------------- decoder rows
+struct RowDesc {
+    int token, pos;
+    int kv_slot;     // self-KV sequence slot
+    int audio_slot;  // cross-KV slot
+};
+template <typename T>
+void launch_embed(const RowDesc* rows, int n_rows, const T* tok_emb, const float* pos_emb, float* x, int d, cudaStream_t s);
+// qkv [n_rows][3d] (q|k|v) -> K/V blocks of one layer: dst = block + kv_slot*slot_stride + pos*d
+template <typename T>
+void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kblock, T* vblock, size_t slot_stride, int d, cudaStream_t s);
+// one (row, head) per block; key j of the row lives at base + slot*slot_stride + j*key_stride + head*64.
+// cross == 0: slot = kv_slot, keys 0..pos (causal);  cross == 1: slot = audio_slot, keys 0..n_keys-1.
+template <typename T>
+void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
+                          int cross, size_t slot_stride, size_t key_stride, int n_keys, cudaStream_t s);
+// self-KV slot copy for beam search: positions [0, n_pos) of each of the n_blocks (layer, K|V) blocks
+struct KvCopy {
+    int src, dst, n_pos;
+};
+template <typename T>
+void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_blocks, size_t block_stride, int d, cudaStream_t s);
+
+// ---------------------------------------------------------------- K6 logits -> token
+struct VocabIds {
+    int n_vocab, eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank, n_lang;
+};
+struct SampleParams {
+    float temperature;
+    int is_initial, last_was_ts, penult_was_ts, has_ts;
+    int suppress_blank, no_timestamps;
+    int ts_initial_limit;  // first suppressed timestamp id on the initial step (n_vocab: none)
+    int ts_min;            // timestamps below this id are suppressed when has_ts
+    int mode;              // 0 argmax, 1 sample with u, 2 top-k
+    int k;
+    int want_nosp;         // compute softmax(raw logits)[nosp]
+    double u;
+};
+struct SampleResult {
+    int id, tid;
+    float p, plog, pt, ptsum, no_speech_prob;
+    int n_topk;
+    int topk_id[kMaxTopK];
+    float topk_plog[kMaxTopK];
+    float topk_p[kMaxTopK];
+};
+// logits [n_rows][ld]; optional dumps of the filtered logprobs / probs (row-major [n_rows][n_vocab])
+void launch_process_logits(const float* logits, int ld, const SampleParams* params, SampleResult* results, int n_rows, const VocabIds& v,
+                           float* logprobs_out, float* probs_out, cudaStream_t s);
+// language detection: softmax over the language-token logits of one row; probs_out [n_lang]
+void launch_lang_probs(const float* logits, const VocabIds& v, float* probs_out, int* best, cudaStream_t s);
+
+// ---------------------------------------------------------------- misc
+template <typename TI, typename TO>
+void launch_convert(const TI* in, TO* out, size_t n, cudaStream_t s);
+// strided 2D copy with conversion: out[r][c] = in[r*ld_in + c]
+template <typename TI, typename TO>
+void launch_convert_2d(const TI* in, size_t ld_in, TO* out, size_t ld_out, int rows, int cols, cudaStream_t s);
+
+long kernel_launch_count();  // process-wide count of kernels launched through these launchers
+void count_launch();
+
+}  // namespace nobs

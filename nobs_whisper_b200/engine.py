@@ -1,0 +1,107 @@
+"""Python mirror of the reference's WhisperEngine (src-tauri/src/whisper.rs:16-260) over the
+C++ host wrapper exported by the library (csrc/host/whisper_engine.cpp, nobs_engine_* shims)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class WhisperEngineError(Exception):
+    pass
+
+
+class LoadError(WhisperEngineError):  # whisper.rs:8-9
+    pass
+
+
+class TranscriptionError(WhisperEngineError):  # whisper.rs:10-11
+    pass
+
+
+class NoModel(WhisperEngineError):  # whisper.rs:12-13
+    pass
+
+
+_ERR = {1: LoadError, 2: TranscriptionError, 3: NoModel}
+
+
+def filter_hallucinations(text: str) -> str:  # whisper.rs:233-260
+    return _lib.lib().nobs_filter_hallucinations(text.encode()).decode()
+
+
+class WhisperEngine:
+    def __init__(self):  # whisper.rs:22-27
+        self._L = _lib.lib()
+        self._h = self._L.nobs_engine_new()
+
+    @classmethod
+    def from_file(cls, model_path: str) -> "WhisperEngine":  # whisper.rs:30-34
+        e = cls()
+        e.load_model(model_path)
+        return e
+
+    def _raise(self, kind: int):
+        raise _ERR[kind](self._L.nobs_engine_last_error(self._h).decode(errors="replace"))
+
+    def load_model(self, model_path: str) -> None:  # whisper.rs:36-52
+        k = self._L.nobs_engine_load_model(self._h, str(model_path).encode())
+        if k:
+            self._raise(k)
+
+    def unload_model(self) -> None:  # whisper.rs:55-59
+        self._L.nobs_engine_unload_model(self._h)
+
+    def is_loaded(self) -> bool:  # whisper.rs:62-64
+        return bool(self._L.nobs_engine_is_loaded(self._h))
+
+    @staticmethod
+    def _s(v):
+        return None if v is None else v.encode()
+
+    def transcribe(self, audio, language=None, vocabulary=None, context=None) -> str:  # whisper.rs:66-148
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        out = C.c_char_p()
+        k = self._L.nobs_engine_transcribe(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), int(a.size), self._s(language),
+                                           self._s(vocabulary), self._s(context), C.byref(out))
+        if k:
+            self._raise(k)
+        return (out.value or b"").decode("utf-8", errors="replace")
+
+    def transcribe_chunked(self, chunks, language=None, vocabulary=None) -> str:  # whisper.rs:152-197
+        arrs = [np.ascontiguousarray(c, dtype=np.float32) for c in chunks]
+        n = len(arrs)
+        ptrs = (C.POINTER(C.c_float) * max(n, 1))(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+        ns = (C.c_int * max(n, 1))(*[int(a.size) for a in arrs])
+        out = C.c_char_p()
+        k = self._L.nobs_engine_transcribe_chunked(self._h, ptrs, ns, n, self._s(language), self._s(vocabulary), C.byref(out))
+        if k:
+            self._raise(k)
+        return (out.value or b"").decode("utf-8", errors="replace")
+
+    def transcribe_batch(self, audios, language=None, vocabulary=None, beam_size: int = 0) -> list[str]:
+        """Independent windows decoded together on the GPU; no context chaining."""
+        arrs = [np.ascontiguousarray(c, dtype=np.float32) for c in audios]
+        n = len(arrs)
+        if n == 0:
+            return []
+        ptrs = (C.POINTER(C.c_float) * n)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+        ns = (C.c_int * n)(*[int(a.size) for a in arrs])
+        texts = (C.c_char_p * n)()
+        k = self._L.nobs_engine_transcribe_batch(self._h, ptrs, ns, n, self._s(language), self._s(vocabulary), int(beam_size), texts)
+        if k:
+            self._raise(k)
+        return [(t or b"").decode("utf-8", errors="replace") for t in texts]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nobs_engine_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
