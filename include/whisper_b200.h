@@ -327,6 +327,12 @@ typedef struct whisper_b200_stats {
 } whisper_b200_stats;
 int whisper_b200_get_stats(struct whisper_state* state, whisper_b200_stats* out);
 
+/* Kernel-level test hook: C[M][N] = epi(A * W^T) through the bf16 tcgen05 GEMM.  A is given as
+ * a_elems fp32 values with row stride lda (lda < K gives the overlapping-row view the stem
+ * convolutions use); inputs are rounded to bf16 on the device.  res: [res_mod ? res_mod : M][N]. */
+int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const float* A, size_t a_elems, const float* W, const float* bias, int act,
+                                 const float* res, int res_mod, int win_rows, int valid_rows, int out_f32, float* C_out);
+
 int whisper_b200_device_count(void);
 const char* whisper_b200_last_error(void);
 

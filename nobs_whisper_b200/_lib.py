@@ -185,6 +185,8 @@ SIGNATURES = {
     "whisper_b200_process_logits": (C.c_int, [vp, WhisperFullParams, fp, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_float,
                                               C.c_int, C.c_double, C.c_int, fp, fp, C.POINTER(B200SampleResult)]),
     "whisper_b200_get_stats": (C.c_int, [vp, C.POINTER(B200Stats)]),
+    "whisper_b200_debug_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, fp]),
     "whisper_b200_device_count": (C.c_int, []),
     "whisper_b200_last_error": (C.c_char_p, []),
     "nobs_engine_new": (vp, []),

@@ -1,9 +1,383 @@
-// Placeholder translation unit: replaced by the tcgen05 implementation (see git history).
+// bf16 GEMM for sm_100a: C[M,N] = epi(A[M,K] * W[N,K]^T), fp32 accumulation.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  shared-memory ring (STAGES x {A 128x64, W BNx64})
+//   tcgen05.mma.cta_group::1.kind::f16 issued by one thread, accumulators in TMEM (2 x BN columns,
+//   double buffered)  ->  tcgen05.ld by 4 epilogue warps  ->  fused bias / GELU / residual /
+//   row-mask epilogue  ->  global (bf16 or fp32).
+//
+// Persistent: one CTA per SM walks a static tile schedule (m fastest, so CTAs that run together
+// share the same weight tile in L2).  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM
+// allocator, 4..7 = epilogue (warp % 4 selects the TMEM lane quadrant).
+//
+// The A operand may be an "overlapping rows" view (row stride smaller than the row length):
+// that is how both stem convolutions run as GEMMs without materialising im2col
+// (conv1: stride n_mels, K = 3*n_mels; conv2: stride 2d, K = 3d).
 #include "gemm_sm100.cuh"
 
+#include <cuda.h>
+
+#include <mutex>
+#include <string>
+
+#include "device_utils.cuh"
+
 namespace nobs {
-static const char* g_err = "bf16 tcgen05 path is not built yet";
-bool launch_gemm_bf16_sm100(const bf16*, int, const bf16*, int, void*, int, bool, int, int, int, const Epilogue&, cudaStream_t) { return false; }
-bool launch_enc_attention_bf16_sm100(const bf16*, bf16*, int, int, int, cudaStream_t) { return false; }
-const char* sm100_last_error() { return g_err; }
+
+namespace {
+
+thread_local std::string g_err;
+
+constexpr int BM = 128;      // UMMA M
+constexpr int BK = 64;       // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A protocol error must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand: 8-row atoms of 1024 B (SBO), LBO unused (1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N x 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <typename TC> struct OutVec;
+template <> struct OutVec<float> {
+    static __device__ __forceinline__ void store8(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct OutVec<bf16> {
+    static __device__ __forceinline__ void store8(bf16* p, const float* v) {
+        uint4 u;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+
+template <int BN> struct Cfg {
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename TC>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TC* C, int ldc, int M, int N,
+                       int K, Epilogue e, int vec_ok) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);  // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + cfg::STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t* empty = full + cfg::STAGES;
+    uint64_t* tfull = empty + cfg::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(&full[stage], cfg::STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_BYTES, &tmap_a, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sB + stage * cfg::B_BYTES, &tmap_b, &full[stage], kb * BK, n_blk * BN);
+                }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(BN);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES), b_addr = smem_u32(sB + stage * cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty[stage]);                    // smem slot is free once these MMAs retire
+                    if (kb == num_k - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> bias / GELU / residual / mask -> global =====
+        const int q = warp & 3;              // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int m = m_blk * BM + row;
+            const bool row_ok = m < M;
+            const bool row_zero = e.win_rows > 0 && (m % e.win_rows) >= e.valid_rows;
+            const float* res_row = nullptr;
+            if (e.res && row_ok) res_row = e.res + (size_t)(e.res_mod > 0 ? m % e.res_mod : m) * e.res_ld;
+            TC* c_row = C + (size_t)m * ldc;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + c0;
+                if (row_ok && n0 < N) {
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + j;
+                        float x = __uint_as_float(v[j]);
+                        if (n < N) {
+                            if (e.bias) x += __ldg(e.bias + n);
+                            if (e.act == 1) x = gelu_tanh_fast(x);
+                            if (res_row) x += res_row[n];
+                        }
+                        o[j] = row_zero ? 0.0f : x;
+                    }
+                    if (vec_ok && n0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) OutVec<TC>::store8(c_row + n0 + j, o + j);
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < N) c_row[n0 + j] = from_f32<TC>(o[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2D bf16 tensor [rows][inner] with an arbitrary (16-byte multiple) row stride; box = 64 x box_rows, 128B swizzle
+bool make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { g_err = "cuTensorMapEncodeTiled is not available"; return false; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * 2) % 16) { g_err = "TMA operand is not 16-byte aligned"; return false; }
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (inner " + std::to_string(inner) + ", rows " +
+                std::to_string(rows) + ", stride " + std::to_string(row_stride_elems) + ")";
+        return false;
+    }
+    return true;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, typename TC>
+bool launch_cfg(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
+    using cfg = Cfg<BN>;
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM)) return false;
+    if (!make_tmap(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN)) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES) != cudaSuccess) {
+            g_err = "cudaFuncSetAttribute(max dynamic smem) failed";
+            return false;
+        }
+        configured = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int vec = (sizeof(TC) == 2 ? 8 : 4);
+    const int vec_ok = (ldc % vec == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    gemm_bf16_sm100_kernel<BN, TC><<<grid, 256, cfg::SMEM_BYTES, s>>>(ta, tb, C, ldc, M, N, K, e, vec_ok);
+    count_launch();
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { g_err = std::string("gemm launch: ") + cudaGetErrorString(err); return false; }
+    return true;
+}
+
+template <typename TC>
+bool dispatch(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
+    const int sms = num_sms(), mt = (M + BM - 1) / BM;
+    auto tiles = [&](int bn) { return mt * ((N + bn - 1) / bn); };
+    // widest tile that still gives every SM work; skinny (decoder) problems fall to BN = 32 so that
+    // the weight stream is spread over as many SMs as possible
+    if (tiles(256) >= sms) return launch_cfg<256, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    if (tiles(128) >= sms) return launch_cfg<128, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    if (tiles(64) >= sms) return launch_cfg<64, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    return launch_cfg<32, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+}
+
+}  // namespace
+
+bool launch_gemm_bf16_sm100(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, bool c_is_f32, int M, int N, int K, const Epilogue& e,
+                            cudaStream_t s) {
+    if (M <= 0 || N <= 0 || K <= 0) return true;
+    if (c_is_f32) return dispatch<float>(A, lda, W, ldw, static_cast<float*>(C), ldc, M, N, K, e, s);
+    return dispatch<bf16>(A, lda, W, ldw, static_cast<bf16*>(C), ldc, M, N, K, e, s);
+}
+
+bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s) {
+    launch_enc_attention_simt<bf16>(qkv, out, n_win, n_head, d, s);
+    return true;
+}
+
+const char* sm100_last_error() { return g_err.c_str(); }
+
 }  // namespace nobs

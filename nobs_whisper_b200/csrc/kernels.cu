@@ -3,6 +3,7 @@
 // logit filter / log-softmax / argmax / sampling / top-k kernel.
 // The tcgen05 (tensor-core) kernels live in gemm_sm100.cu / attention_sm100.cu.
 #include "kernels.cuh"
+#include "device_utils.cuh"
 
 #include <atomic>
 #include <climits>
@@ -14,61 +15,6 @@ static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define NOBS_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
-
-// ------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_f32(float v) { return v; }
-__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
-template <typename T> __device__ __forceinline__ T from_f32(float v);
-template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
-
-__device__ __forceinline__ float gelu_tanh(float x) {
-    // ggml GELU: 0.5*x*(1 + tanh(sqrt(2/pi)*x*(1 + 0.044715*x^2)))
-    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
-}
-
-__device__ __forceinline__ int float_key(float f) {  // order-preserving float -> int
-    int b = __float_as_int(f);
-    return b >= 0 ? b : b ^ 0x7fffffff;
-}
-__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block-wide reductions (blockDim.x multiple of 32, <= 1024); `red` holds >= 32 elements
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, T ident, Op op, T* red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();  // protect `red` from a previous use
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    v = lane < nw ? red[lane] : ident;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;  // every thread holds the result
-}
-struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
-struct OpAddF { __device__ float operator()(float a, float b) const { return a + b; } };
-struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
-struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
 
 // ------------------------------------------------------------------------------------------
 // K1: log-mel.  One warp per frame: windowed samples -> 16 x DFT-25 -> 4 radix-2 stages in
@@ -240,18 +186,6 @@ void launch_export_mel(const float* raw, const int* max_key, int n_frames, int n
 // ------------------------------------------------------------------------------------------
 // fp32 GEMM (parity mode): C = epi(A * W^T), 128x128x16 tiles, 8x8 per thread.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const Epilogue& e) {
-    float v = acc;
-    if (e.bias) v += __ldg(e.bias + n);
-    if (e.act == 1) v = gelu_tanh(v);
-    if (e.res) {
-        const int rm = e.res_mod > 0 ? m % e.res_mod : m;
-        v += e.res[(size_t)rm * e.res_ld + n];
-    }
-    if (e.win_rows > 0 && (m % e.win_rows) >= e.valid_rows) v = 0.0f;
-    return v;
-}
-
 constexpr int GB_M = 128, GB_N = 128, GB_K = 16;
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
@@ -361,7 +295,28 @@ template void launch_layernorm_gather<bf16>(const float*, int, const int*, const
 // ------------------------------------------------------------------------------------------
 constexpr int EA_BQ = 64, EA_BK = 64, EA_DH = 64;
 
-__global__ void __launch_bounds__(256) enc_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int d, int n_valid) {
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) enc_attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int d, int n_valid) {
     extern __shared__ __align__(16) float ea_smem[];
     float (*Qs)[EA_DH + 4] = reinterpret_cast<float (*)[EA_DH + 4]>(ea_smem);                              // [64][68]
     float (*Kt)[EA_BK + 4] = reinterpret_cast<float (*)[EA_BK + 4]>(ea_smem + EA_BQ * (EA_DH + 4));          // [dh][64+4]
@@ -371,14 +326,14 @@ __global__ void __launch_bounds__(256) enc_attention_f32_kernel(const float* __r
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
     const size_t ld = (size_t)3 * d;
-    const float* base = qkv + (size_t)w * kWinRows * ld;
-    const float* Qg = base + (size_t)qt * EA_BQ * ld + h * EA_DH;
-    const float* Kg = base + d + h * EA_DH;
-    const float* Vg = base + 2 * d + h * EA_DH;
+    const T* base = qkv + (size_t)w * kWinRows * ld;
+    const T* Qg = base + (size_t)qt * EA_BQ * ld + h * EA_DH;
+    const T* Kg = base + d + h * EA_DH;
+    const T* Vg = base + 2 * d + h * EA_DH;
 
     for (int i = tid; i < EA_BQ * EA_DH / 4; i += 256) {
         const int r = i >> 4, c = (i & 15) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(Qg + (size_t)r * ld + c);
+        const float4 v = load4<T>(Qg + (size_t)r * ld + c);
         *reinterpret_cast<float4*>(&Qs[r][c]) = v;
     }
     float m_i[4], l_i[4], O[4][4];
@@ -397,8 +352,8 @@ __global__ void __launch_bounds__(256) enc_attention_f32_kernel(const float* __r
             const int key = kt * EA_BK + r;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
             if (key < n_valid) {
-                kv = *reinterpret_cast<const float4*>(Kg + (size_t)key * ld + c);
-                vv = *reinterpret_cast<const float4*>(Vg + (size_t)key * ld + c);
+                kv = load4<T>(Kg + (size_t)key * ld + c);
+                vv = load4<T>(Vg + (size_t)key * ld + c);
             }
             Kt[c + 0][r] = kv.x; Kt[c + 1][r] = kv.y; Kt[c + 2][r] = kv.z; Kt[c + 3][r] = kv.w;
             *reinterpret_cast<float4*>(&Vs[r][c]) = vv;
@@ -469,21 +424,27 @@ __global__ void __launch_bounds__(256) enc_attention_f32_kernel(const float* __r
     for (int i = 0; i < 4; ++i) {
         const float inv = 1.0f / l_i[i];
         const size_t row = (size_t)w * kWinRows + qt * EA_BQ + ty * 4 + i;
-        *reinterpret_cast<float4*>(out + row * d + h * EA_DH + tx * 4) = make_float4(O[i][0] * inv, O[i][1] * inv, O[i][2] * inv, O[i][3] * inv);
+        store4(out + row * d + h * EA_DH + tx * 4, make_float4(O[i][0] * inv, O[i][1] * inv, O[i][2] * inv, O[i][3] * inv));
     }
 }
 
-void launch_enc_attention_f32(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s) {
+template <typename T>
+void launch_enc_attention_simt(const T* qkv, T* out, int n_win, int n_head, int d, cudaStream_t s) {
     if (n_win <= 0) return;
     const int smem = 4 * EA_BQ * (EA_DH + 4) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(enc_attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(enc_attention_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     dim3 grid(kWinRows / EA_BQ, n_head, n_win);
-    enc_attention_f32_kernel<<<grid, 256, smem, s>>>(qkv, out, d, 1500);
+    enc_attention_simt_kernel<T><<<grid, 256, smem, s>>>(qkv, out, d, 1500);
     NOBS_COUNT_LAUNCH();
+}
+template void launch_enc_attention_simt<float>(const float*, float*, int, int, int, cudaStream_t);
+template void launch_enc_attention_simt<bf16>(const bf16*, bf16*, int, int, int, cudaStream_t);
+void launch_enc_attention_f32(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s) {
+    launch_enc_attention_simt<float>(qkv, out, n_win, n_head, d, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -74,6 +74,9 @@ void launch_layernorm_gather(const float* x, int ldx, const int* idx, const floa
 // ---------------------------------------------------------------- encoder attention (non-causal, 1500 keys)
 // qkv: [n_win*kWinRows][3*d] (q | k | v), out: [n_win*kWinRows][d]
 void launch_enc_attention_f32(const float* qkv, float* out, int n_win, int n_head, int d, cudaStream_t s);
+// CUDA-core flash-style kernel (fp32 math), storage type T
+template <typename T>
+void launch_enc_attention_simt(const T* qkv, T* out, int n_win, int n_head, int d, cudaStream_t s);
 
 // ---------------------------------------------------------------- decoder rows
 struct RowDesc {
