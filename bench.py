@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds transcribed per wall-second (BASELINE.json `metric`).
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): whisper
+large-v3 (128 mel bins, 32+32 layers), bf16, one hour of synthetic 16 kHz audio cut into
+120 independent 30-s windows, greedy decode with the reference's parameter block
+(src-tauri/src/whisper.rs:88-124: temperature fallback on, suppress_blank, thresholds).
+Random-init weights of the named architecture written as a ggml f16 file (no network here).
+
+One "step" = one pass of the hot path (mel -> encoder -> cross-KV -> decoder loop with
+fallback -> segment text) over the rank's 120 windows.  N > 1: one process per GPU, every rank
+transcribes its own 120 windows (weak scaling, no collective on the data path; only a barrier
+and a max-reduce of the times), `value` = all ranks' audio-seconds / max-over-ranks time.
+
+  value  : inputs already resident in HBM (device PCM), timed on the device-side wall
+           (barrier + cuda synchronize both sides)
+  e2e    : the same through the public host API (WhisperEngine.transcribe_batch over pinned
+           host PCM): H2D of the PCM and D2H of the transcripts are inside the timed region.
+  roofline: the dominant kernel (bf16 tcgen05 GEMM, encoder side): algorithmic FLOPs / summed
+           per-launch CUDA-event durations recorded inside the timed steps.
+  cpu_baseline: the oracle (CPU restatement of the reference path) on a bounded sample.
+
+`--impl reference` times the reference's own CPU path.  whisper-rs / whisper.cpp are not
+vendored in /root/reference and cannot be built offline, so this arm runs the oracle port
+(oracle/) on the host cores — the one place besides tests/ and smoke() that executes oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_DIR = os.environ.get("NOBS_BENCH_MODEL_DIR", "/tmp/nobs_whisper_models")
+WINDOW_S = 30.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tf_burst": d.get("bf16_tflops", 1590.0),
+                "tf_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def gemm_flops_per_window(a) -> float:
+    """Algorithmic GEMM FLOPs of one window on the encoder side: both stem
+    convolutions, QKV/out/MLP of every encoder layer, cross-KV projections of every decoder layer."""
+    d, nm = a.n_audio_state, a.n_mels
+    return (2.0 * 3000 * 3 * nm * d + 2.0 * 1500 * 3 * d * d + a.n_audio_layer * 24.0 * 1500 * d * d
+            + a.n_text_layer * 4.0 * 1500 * d * d)
+
+
+def attn_flops_per_window(a) -> float:
+    return a.n_audio_layer * 4.0 * 1500 * 1500 * a.n_audio_state
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ensure_model(arch: str, rank: int, world: int, barrier) -> str:
+    from nobs_whisper_b200 import ggml_synth
+    path = ggml_synth.model_path(MODEL_DIR, arch, seed=0, ftype=1, init="survey")
+    if rank == 0 and not os.path.exists(path):
+        ggml_synth.ensure_model(MODEL_DIR, arch, seed=0, ftype=1, init="survey")
+    barrier()
+    return path
+
+
+def make_audio(n_windows: int, first: int):
+    from nobs_whisper_b200 import synth_audio
+    return [synth_audio.synth_clip(first + i, WINDOW_S) for i in range(n_windows)]
+
+
+def run_reference(args, rank, world, arch_name):
+    """--impl reference: the oracle port on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from nobs_whisper_b200 import ggml_synth
+    from oracle import oracle
+    path = ensure_model(arch_name, 0, 1, lambda: None)
+    orc = oracle.Oracle(path)
+    cores = oracle.lib().wo_max_threads()
+    n_sample = args.cpu_windows
+    audio = make_audio(n_sample, 0)
+    prm = oracle.reference_params("en")
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for a in audio:
+            orc.full(prm, a)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = args.steps * n_sample * WINDOW_S / total
+    sample = f"{n_sample} window(s) of {WINDOW_S:.0f} s per step (of the 120-window workload), oracle port of the whisper-rs CPU path, fp32"
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whisper {arch_name}, 120 x 30-s windows (1 h synthetic 16 kHz audio), greedy + temperature fallback; CPU arm times a bounded sample",
+                   "windows_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default=os.environ.get("NOBS_BENCH_MODEL", "large-v3"))
+    ap.add_argument("--windows", type=int, default=120)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-windows", type=int, default=1, help="bounded sample for the CPU arm / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world, args.model)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import ggml_synth
+
+    arch = ggml_synth.ARCHS[args.model]
+    path = ensure_model(args.model, rank, world, barrier)
+    os.environ["NOBS_WHISPER_PRECISION"] = args.precision
+    ctxp_device = local_rank
+
+    # the public host API (mirror of the reference's WhisperEngine); the context lands on this rank's GPU
+    os.environ["NOBS_WHISPER_DEVICE"] = str(ctxp_device)
+    eng = nw.WhisperEngine()
+    eng.load_model(path)
+    eng.set_profiling(True)
+
+    n_win = args.windows
+    audio = make_audio(n_win, rank * n_win)
+    n_samples = [len(a) for a in audio]
+    # pinned host copies (e2e arm) and device copies (HBM-resident arm)
+    host = [torch.from_numpy(a).pin_memory() for a in audio]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    torch.cuda.synchronize()
+    h2d_bytes = int(sum(n_samples) * 4)
+
+    def step(tensors):
+        texts = eng.transcribe_batch_ptrs([t.data_ptr() for t in tensors], n_samples, language="en")
+        return texts, eng.last_stats()
+
+    def timed(tensors, steps, warmup):
+        for _ in range(warmup):
+            step(tensors)
+        barrier()
+        torch.cuda.synchronize()
+        agg = {"launches": 0, "gemm_ms": 0.0, "gemm_n": 0, "attn_ms": 0.0, "attn_n": 0, "rows": 0, "samples": 0, "windows": 0, "fallbacks": 0,
+               "ms_mel": 0.0, "ms_enc": 0.0, "ms_dec": 0.0, "rounds": 0, "d2h": 0}
+        t0 = time.perf_counter()
+        eng.event_record(0)  # CUDA events on the stream the kernels are launched on
+        for _ in range(steps):
+            texts, s = step(tensors)
+            agg["launches"] += s.n_kernel_launches; agg["gemm_ms"] += s.gpu_ms_enc_gemm; agg["gemm_n"] += s.n_enc_gemm
+            agg["attn_ms"] += s.gpu_ms_enc_attn; agg["attn_n"] += s.n_enc_attn; agg["rows"] += s.n_decode_rows
+            agg["samples"] += s.n_sample_rows; agg["windows"] += s.n_windows; agg["fallbacks"] += s.n_fallbacks
+            agg["ms_mel"] += s.gpu_ms_mel; agg["ms_enc"] += s.gpu_ms_encode; agg["ms_dec"] += s.gpu_ms_decode
+            agg["rounds"] += s.n_decode_rounds
+            agg["d2h"] += sum(len(t.encode()) for t in texts) + 48 * s.n_sample_rows  # transcripts + per-step sample results
+        eng.event_record(1)
+        dt_dev_ms = eng.event_elapsed_ms(0, 1)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dt = dt_dev_ms / 1e3 if dt_dev_ms > 0 else wall
+        agg["wall_s"] = wall
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        barrier()
+        return dt, agg, texts
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dt_dev, agg_dev, _ = timed(dev, args.steps, args.warmup)
+    dt_e2e, agg_e2e, texts = timed(host, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    audio_s_per_step = n_win * WINDOW_S * world
+    value = args.steps * audio_s_per_step / dt_dev
+    e2e = args.steps * audio_s_per_step / dt_e2e
+
+    if rank == 0:
+        peaks = load_peaks()
+        gemm_flops = gemm_flops_per_window(arch) * agg_dev["windows"]
+        gemm_s = agg_dev["gemm_ms"] / 1e3
+        achieved = gemm_flops / gemm_s / 1e12 if gemm_s > 0 else 0.0
+        peak = peaks["tf_sustained"]
+        attn_tf = attn_flops_per_window(arch) * agg_dev["windows"] / (agg_dev["attn_ms"] / 1e3) / 1e12 if agg_dev["attn_ms"] > 0 else 0.0
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle
+            orc = oracle.Oracle(path)
+            prm = oracle.reference_params("en")
+            t0 = time.perf_counter()
+            for a in audio[: args.cpu_windows]:
+                orc.full(prm, a)
+            cdt = time.perf_counter() - t0
+            cpu_baseline = {"value": args.cpu_windows * WINDOW_S / cdt, "unit": "audio-s/s", "cores": oracle.lib().wo_max_threads(), "kind": "port",
+                            "sample": f"first {args.cpu_windows} of the {n_win} windows ({args.cpu_windows * WINDOW_S:.0f} s of audio), oracle port of the "
+                                      f"whisper-rs CPU path in fp32, {cdt:.1f} s of CPU work"}
+            orc.close()
+        steps = args.steps
+        line = {
+            "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {
+                "workload": f"whisper {args.model} ({arch.n_mels} mel bins, {arch.n_audio_layer}+{arch.n_text_layer} layers) {args.precision}, "
+                            f"{n_win} x 30-s windows per GPU (1 h synthetic 16 kHz audio), greedy best_of=1 with the reference's temperature fallback",
+                "windows_per_gpu": n_win, "weights": "random-init N(0,0.02) ggml f16 file, seed 0", "l2": "inputs and weights exceed L2 (3.1 GB weights, 30 GB cross-KV)",
+                "decoder_rows_per_step": agg_dev["rows"] / steps, "sampled_tokens_per_step": agg_dev["samples"] / steps,
+                "decoder_rounds_per_step": agg_dev["rounds"] / steps, "fallbacks_per_step": agg_dev["fallbacks"] / steps,
+                "stage_ms_per_step": {"mel": agg_dev["ms_mel"] / steps, "encode": agg_dev["ms_enc"] / steps, "decode": agg_dev["ms_dec"] / steps},
+                "x_realtime": value, "timing": "CUDA events on the library stream around the K steps, max over ranks",
+                "host_wall_ms_per_step": 1000.0 * agg_dev["wall_s"] / steps,
+            },
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int(agg_e2e["d2h"] / steps) * world,
+                    "ms_per_step": 1000.0 * dt_e2e / steps},
+            "gpu_launches": int(agg_dev["launches"] + agg_e2e["launches"]),
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_sm100_kernel (encoder-side GEMMs: conv stem, QKV/out/MLP, cross-KV)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": agg_dev["gemm_n"],
+                         "share_of_step": agg_dev["gemm_ms"] / (1000.0 * dt_dev) if dt_dev else None,
+                         "encoder_attention": {"achieved_tflops": attn_tf, "ms_per_step": agg_dev["attn_ms"] / steps, "launches": agg_dev["attn_n"]}},
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

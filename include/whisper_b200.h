@@ -196,7 +196,8 @@ struct whisper_full_params whisper_full_default_params(enum whisper_sampling_str
 /* whisper.rs:127-129 state.full(params, audio): mel -> [language detect] -> per window
  * encode / decode with temperature fallback -> segments.  0 = ok; non-zero = error
  * (whisper-rs maps -1 UnableToCalculateSpectrogram, 7 FailedToEncode, 8 FailedToDecode).
- * `samples` is borrowed for the call; language / initial_prompt are borrowed C strings. */
+ * `samples` is borrowed for the call (host memory — pinned or pageable — or device memory: it is
+ * read with cudaMemcpyDefault); language / initial_prompt are borrowed C strings. */
 int whisper_full_with_state(struct whisper_context* ctx, struct whisper_state* state, struct whisper_full_params params,
                             const float* samples, int n_samples);
 
@@ -324,7 +325,13 @@ typedef struct whisper_b200_stats {
     int64_t n_fallbacks;      /* temperature fallbacks */
     int64_t n_kernel_launches;/* kernels launched by the batch this audio was part of */
     double gpu_ms_mel, gpu_ms_encode, gpu_ms_decode; /* CUDA-event stage times of that batch */
+    /* with profiling on: summed per-launch CUDA-event durations and launch counts of the encoder-side
+     * GEMM kernel (conv stem, QKV/out/MLP, cross-KV projection) and of the encoder attention kernel */
+    double gpu_ms_enc_gemm, gpu_ms_enc_attn;
+    int64_t n_enc_gemm, n_enc_attn;
 } whisper_b200_stats;
+/* Record a CUDA-event pair around every encoder GEMM / attention launch (costs ~1 us per launch). */
+void whisper_b200_set_profiling(struct whisper_context* ctx, int on);
 int whisper_b200_get_stats(struct whisper_state* state, whisper_b200_stats* out);
 
 /* Kernel-level test hook: C[M][N] = epi(A * W^T) through the bf16 tcgen05 GEMM.  A is given as
@@ -332,6 +339,10 @@ int whisper_b200_get_stats(struct whisper_state* state, whisper_b200_stats* out)
  * convolutions use); inputs are rounded to bf16 on the device.  res: [res_mod ? res_mod : M][N]. */
 int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const float* A, size_t a_elems, const float* W, const float* bias, int act,
                                  const float* res, int res_mod, int win_rows, int valid_rows, int out_f32, float* C_out);
+
+/* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */
+int whisper_b200_event_record(struct whisper_context* ctx, int slot);
+double whisper_b200_event_elapsed_ms(struct whisper_context* ctx, int slot_a, int slot_b);
 
 int whisper_b200_device_count(void);
 const char* whisper_b200_last_error(void);
@@ -358,6 +369,10 @@ int nobs_engine_transcribe_chunked(struct nobs_engine* e, const float* const* ch
 int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audios, const int* n, int n_audios, const char* language,
                                  const char* vocabulary, int beam_size, const char** texts);
 const char* nobs_engine_last_error(struct nobs_engine* e);
+/* counters of the engine's last transcribe / transcribe_batch call, summed over its audios */
+int nobs_engine_last_stats(struct nobs_engine* e, whisper_b200_stats* out);
+/* the loaded context (NULL if none), e.g. for whisper_b200_set_profiling */
+struct whisper_context* nobs_engine_context(struct nobs_engine* e);
 /* whisper.rs:233-260; returns a pointer to a thread-local buffer */
 const char* nobs_filter_hallucinations(const char* text);
 

@@ -108,6 +108,7 @@ class B200Stats(C.Structure):
         ("n_windows", C.c_int64), ("n_decode_rounds", C.c_int64), ("n_decode_rows", C.c_int64),
         ("n_sample_rows", C.c_int64), ("n_fallbacks", C.c_int64), ("n_kernel_launches", C.c_int64),
         ("gpu_ms_mel", C.c_double), ("gpu_ms_encode", C.c_double), ("gpu_ms_decode", C.c_double),
+        ("gpu_ms_enc_gemm", C.c_double), ("gpu_ms_enc_attn", C.c_double), ("n_enc_gemm", C.c_int64), ("n_enc_attn", C.c_int64),
     ]
 
 
@@ -187,6 +188,9 @@ SIGNATURES = {
     "whisper_b200_get_stats": (C.c_int, [vp, C.POINTER(B200Stats)]),
     "whisper_b200_debug_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp]),
+    "whisper_b200_set_profiling": (None, [vp, C.c_int]),
+    "whisper_b200_event_record": (C.c_int, [vp, C.c_int]),
+    "whisper_b200_event_elapsed_ms": (C.c_double, [vp, C.c_int, C.c_int]),
     "whisper_b200_device_count": (C.c_int, []),
     "whisper_b200_last_error": (C.c_char_p, []),
     "nobs_engine_new": (vp, []),
@@ -198,6 +202,8 @@ SIGNATURES = {
     "nobs_engine_transcribe_chunked": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]),
     "nobs_engine_transcribe_batch": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
     "nobs_engine_last_error": (C.c_char_p, [vp]),
+    "nobs_engine_last_stats": (C.c_int, [vp, C.POINTER(B200Stats)]),
+    "nobs_engine_context": (vp, [vp]),
     "nobs_filter_hallucinations": (C.c_char_p, [C.c_char_p]),
 }
 

@@ -38,6 +38,7 @@ struct whisper_context_params whisper_context_default_params(void) {
     p.use_gpu = true;
     p.flash_attn = false;
     p.gpu_device = 0;
+    if (const char* dev = getenv("NOBS_WHISPER_DEVICE")) p.gpu_device = atoi(dev);  // one process per GPU: LOCAL_RANK
     p.dtw_token_timestamps = false;
     p.dtw_aheads_preset = WHISPER_AHEADS_NONE;
     p.dtw_n_top = -1;
@@ -380,6 +381,21 @@ int whisper_b200_get_stats(struct whisper_state* st, whisper_b200_stats* out) {
     if (!st || !out) return -1;
     *out = st->stats;
     return 0;
+}
+
+void whisper_b200_set_profiling(struct whisper_context* ctx, int on) {
+    if (ctx && ctx->engine) ctx->engine->profiling = on != 0;
+}
+
+int whisper_b200_event_record(struct whisper_context* ctx, int slot) {
+    if (!ctx || !ctx->engine) return -1;
+    std::lock_guard<std::mutex> lock(ctx->engine->mu);
+    return ctx->engine->event_record(slot) ? 0 : -1;
+}
+double whisper_b200_event_elapsed_ms(struct whisper_context* ctx, int slot_a, int slot_b) {
+    if (!ctx || !ctx->engine) return -1.0;
+    std::lock_guard<std::mutex> lock(ctx->engine->mu);
+    return ctx->engine->event_elapsed_ms(slot_a, slot_b);
 }
 
 int whisper_b200_device_count(void) {

@@ -81,6 +81,8 @@ public:
         if (encout_pool_) cudaFree(encout_pool_);
         if (pcm_dev_) cudaFree(pcm_dev_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_pool_) cudaEventDestroy(e);
+        for (auto& e : user_ev_) if (e) cudaEventDestroy(e);
         if (stream_) cudaStreamDestroy(stream_);
     }
 
@@ -170,7 +172,7 @@ public:
                 }
             }
             CUDA_OK(cudaMemcpyAsync(m.max_key, &init_key_, sizeof(int), cudaMemcpyHostToDevice, stream_));
-            if (ns > 0) CUDA_OK(cudaMemcpyAsync(pcm_dev_ + off[i], r.pcm, (size_t)ns * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            if (ns > 0) CUDA_OK(cudaMemcpyAsync(pcm_dev_ + off[i], r.pcm, (size_t)ns * sizeof(float), cudaMemcpyDefault, stream_));
             jobs[i] = MelJob{pcm_dev_ + off[i], ns, m.n_frames, m.raw, m.max_key};
             max_frames = std::max(max_frames, m.n_frames);
         }
@@ -200,7 +202,40 @@ public:
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
         stats.ms_encode += ms;
+        collect_marks();
         return true;
+    }
+
+    // ---- per-launch event timing (profiling mode)
+    void mark_begin() {
+        if (!profiling) return;
+        if (ev_used_ + 2 > ev_pool_.size()) {
+            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev_pool_.push_back(e); }
+        }
+        cudaEventRecord(ev_pool_[ev_used_], stream_);
+    }
+    void mark_end(int cls) {
+        if (!profiling) return;
+        cudaEventRecord(ev_pool_[ev_used_ + 1], stream_);
+        marks_.push_back({cls, (int)ev_used_});
+        ev_used_ += 2;
+    }
+    void collect_marks() {  // call after the stream has been synchronised
+        for (const auto& m : marks_) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_pool_[m.second], ev_pool_[m.second + 1]);
+            if (m.first == 0) { stats.ms_enc_gemm += ms; stats.n_enc_gemm++; }
+            else { stats.ms_enc_attn += ms; stats.n_enc_attn++; }
+        }
+        marks_.clear();
+        ev_used_ = 0;
+    }
+    template <typename TA, typename TC>
+    bool tgemm(const TA* A, int lda, const TA* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e) {
+        mark_begin();
+        const bool ok = gemm(A, lda, W, ldw, C, ldc, M, N, K, e, stream_);
+        mark_end(0);
+        return ok;
     }
 
     bool encode_batch(const EncodeRequest* reqs, int nb) {
@@ -222,23 +257,25 @@ public:
         {
             Epilogue e;
             e.bias = conv1_b_; e.act = 1; e.win_rows = kWinRowsIn; e.valid_rows = 3000;
-            if (!gemm(e_mel_, nm, conv1_w_, 3 * nm, e_h1_ + d, d, nb * kWinRowsIn, d, 3 * nm, e, stream_)) return gemm_fail();
+            if (!tgemm(e_mel_, nm, conv1_w_, 3 * nm, e_h1_ + d, d, nb * kWinRowsIn, d, 3 * nm, e)) return gemm_fail();
         }
         // conv2 (stride 2): row (w, t') reads h1 rows 2t'-1..2t'+1 in place (row stride 2d, K = 3d); + positional embedding
         {
             Epilogue e;
             e.bias = conv2_b_; e.act = 1; e.res = enc_pos_; e.res_ld = d; e.res_mod = kWinRows;
-            if (!gemm(e_h1_, 2 * d, conv2_w_, 3 * d, e_x_, d, M, d, 3 * d, e, stream_)) return gemm_fail();
+            if (!tgemm(e_h1_, 2 * d, conv2_w_, 3 * d, e_x_, d, M, d, 3 * d, e)) return gemm_fail();
         }
         for (int l = 0; l < hp_.n_audio_layer; ++l) {
             const Layer<T>& L = enc_[l];
             launch_layernorm<T>(e_x_, d, L.ln1_g, L.ln1_b, e_y_, d, M, d, stream_);
-            { Epilogue e; e.bias = L.bqkv; if (!gemm(e_y_, d, L.wqkv, d, e_qkv_, 3 * d, M, 3 * d, d, e, stream_)) return gemm_fail(); }
+            { Epilogue e; e.bias = L.bqkv; if (!tgemm(e_y_, d, L.wqkv, d, e_qkv_, 3 * d, M, 3 * d, d, e)) return gemm_fail(); }
+            mark_begin();
             if (!enc_attention(e_qkv_, e_att_, nb, hp_.n_audio_head, d, stream_)) return gemm_fail();
-            { Epilogue e; e.bias = L.bo; e.res = e_x_; e.res_ld = d; if (!gemm(e_att_, d, L.wo, d, e_x_, d, M, d, d, e, stream_)) return gemm_fail(); }
+            mark_end(1);
+            { Epilogue e; e.bias = L.bo; e.res = e_x_; e.res_ld = d; if (!tgemm(e_att_, d, L.wo, d, e_x_, d, M, d, d, e)) return gemm_fail(); }
             launch_layernorm<T>(e_x_, d, L.ln2_g, L.ln2_b, e_y_, d, M, d, stream_);
-            { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(e_y_, d, L.w1, d, e_h_, 4 * d, M, 4 * d, d, e, stream_)) return gemm_fail(); }
-            { Epilogue e; e.bias = L.b2; e.res = e_x_; e.res_ld = d; if (!gemm(e_h_, 4 * d, L.w2, 4 * d, e_x_, d, M, d, 4 * d, e, stream_)) return gemm_fail(); }
+            { Epilogue e; e.bias = L.b1; e.act = 1; if (!tgemm(e_y_, d, L.w1, d, e_h_, 4 * d, M, 4 * d, d, e)) return gemm_fail(); }
+            { Epilogue e; e.bias = L.b2; e.res = e_x_; e.res_ld = d; if (!tgemm(e_h_, 4 * d, L.w2, 4 * d, e_x_, d, M, d, 4 * d, e)) return gemm_fail(); }
         }
         launch_layernorm<T>(e_x_, d, enc_lnp_g_, enc_lnp_b_, e_y_, d, M, d, stream_);
         // keep the encoder output per audio slot, then project every decoder layer's cross K/V
@@ -404,6 +441,22 @@ public:
         CUDA_OK(cudaStreamSynchronize(stream_));
         CUDA_OK(cudaGetLastError());
         return true;
+    }
+
+    bool event_record(int slot) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (slot < 0 || slot >= 8) return false;
+        if (!user_ev_[slot]) CUDA_OK(cudaEventCreate(&user_ev_[slot]));
+        CUDA_OK(cudaEventRecord(user_ev_[slot], stream_));
+        return true;
+    }
+    double event_elapsed_ms(int a, int b) override {
+        if (a < 0 || a >= 8 || b < 0 || b >= 8 || !user_ev_[a] || !user_ev_[b]) return -1.0;
+        cudaSetDevice(device_);
+        if (cudaEventSynchronize(user_ev_[b]) != cudaSuccess) return -1.0;
+        float ms = -1.0f;
+        if (cudaEventElapsedTime(&ms, user_ev_[a], user_ev_[b]) != cudaSuccess) return -1.0;
+        return ms;
     }
 
     // ------------------------------------------------------------------ inspection
@@ -760,6 +813,10 @@ private:
     float* d_logits_ = nullptr;
     int last_logit_rows_ = 0;
 
+    cudaEvent_t user_ev_[8] = {};
+    std::vector<cudaEvent_t> ev_pool_;
+    size_t ev_used_ = 0;
+    std::vector<std::pair<int, int>> marks_;
     char* pin_ = nullptr;
     size_t pin_cap_ = 0;
     char* dev_scratch_ = nullptr;

@@ -49,6 +49,9 @@ struct EncodeRequest {
 
 struct EngineStats {
     double ms_mel = 0, ms_encode = 0, ms_decode = 0;
+    // per-launch CUDA-event timing of the encoder's kernel classes (only when profiling is on)
+    double ms_enc_gemm = 0, ms_enc_attn = 0;
+    long n_enc_gemm = 0, n_enc_attn = 0;
     long n_launches = 0;
 };
 
@@ -58,6 +61,7 @@ public:
     static Engine* create(const HostModel& hm, int device, Precision prec, std::string& err);
 
     std::mutex mu;  // one `full` batch at a time per context
+    bool profiling = false;  // record an event pair around every encoder GEMM / attention launch
     Precision precision() const { return prec_; }
     int device() const { return device_; }
     const std::string& last_error() const { return err_; }
@@ -83,6 +87,9 @@ public:
     virtual bool kv_copy(const std::vector<KvCopy>& pairs) = 0;
     // stage-parity hook: run K6 on host-supplied logits
     virtual bool process_logits_host(const float* logits, const SampleParams& sp, SampleResult& out, float* logprobs, float* probs) = 0;
+
+    virtual bool event_record(int slot) = 0;                 // on the engine's stream
+    virtual double event_elapsed_ms(int a, int b) = 0;       // synchronises on event b
 
     virtual bool export_mel(const DeviceMel& m, float* out) = 0;                       // [n_mel][n_len]
     virtual bool export_encoder_output(int audio_slot, float* out) = 0;                 // [1500][d]

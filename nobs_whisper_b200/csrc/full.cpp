@@ -161,6 +161,10 @@ public:
             s.gpu_ms_mel = eng_.stats.ms_mel;
             s.gpu_ms_encode = eng_.stats.ms_encode;
             s.gpu_ms_decode = eng_.stats.ms_decode;
+            s.gpu_ms_enc_gemm = eng_.stats.ms_enc_gemm;
+            s.gpu_ms_enc_attn = eng_.stats.ms_enc_attn;
+            s.n_enc_gemm = eng_.stats.n_enc_gemm;
+            s.n_enc_attn = eng_.stats.n_enc_attn;
         }
         return 0;
     }

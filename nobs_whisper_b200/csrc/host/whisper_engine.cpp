@@ -175,6 +175,17 @@ static std::string collect_text(whisper_state* st) {
     return result;
 }
 
+void WhisperEngine::accumulate_stats(whisper_state* st, bool first) const {
+    whisper_b200_stats s{};
+    if (whisper_b200_get_stats(st, &s) != 0) return;
+    if (first) { last_stats_ = s; return; }
+    last_stats_.n_windows += s.n_windows;
+    last_stats_.n_decode_rows += s.n_decode_rows;
+    last_stats_.n_sample_rows += s.n_sample_rows;
+    last_stats_.n_fallbacks += s.n_fallbacks;
+    last_stats_.n_decode_rounds = std::max(last_stats_.n_decode_rounds, s.n_decode_rounds);
+}
+
 WhisperError WhisperEngine::transcribe(const float* audio, int n, const std::optional<std::string>& language,
                                        const std::optional<std::string>& vocabulary, const std::optional<std::string>& context,
                                        std::string& out) const {
@@ -194,6 +205,7 @@ WhisperError WhisperEngine::transcribe(const float* audio, int n, const std::opt
         return WhisperError{WhisperError::TranscriptionError, "whisper_full_with_state returned " + std::to_string(rc) + ": " + whisper_b200_last_error()};
     }
     out = filter_hallucinations(trim(collect_text(st)));                             // whisper.rs:143-144
+    accumulate_stats(st, true);
     whisper_free_state(st);
     return WhisperError{};
 }
@@ -245,7 +257,10 @@ WhisperError WhisperEngine::transcribe_batch(const std::vector<const float*>& au
         return WhisperError{WhisperError::TranscriptionError, "whisper_b200_full_batch returned " + std::to_string(bad) + ": " + whisper_b200_last_error()};
     }
     out.resize(cnt);
-    for (int i = 0; i < cnt; ++i) out[i] = filter_hallucinations(trim(collect_text(states[i])));
+    for (int i = 0; i < cnt; ++i) {
+        out[i] = filter_hallucinations(trim(collect_text(states[i])));
+        accumulate_stats(states[i], i == 0);
+    }
     free_states();
     return WhisperError{};
 }
@@ -303,6 +318,12 @@ int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audi
     return (int)err.kind;
 }
 const char* nobs_engine_last_error(struct nobs_engine* e) { return e->last_error.c_str(); }
+int nobs_engine_last_stats(struct nobs_engine* e, whisper_b200_stats* out) {
+    if (!e || !out) return -1;
+    *out = e->engine.last_stats();
+    return 0;
+}
+struct whisper_context* nobs_engine_context(struct nobs_engine* e) { return e ? e->engine.raw_context() : nullptr; }
 const char* nobs_filter_hallucinations(const char* text) {
     static thread_local std::string buf;
     buf = nobs::filter_hallucinations(text ? text : "");

@@ -46,12 +46,16 @@ public:
                                   const std::optional<std::string>& vocabulary, int beam_size, std::vector<std::string>& out) const;
 
     whisper_context* raw_context() const { return ctx_; }
+    // counters of the last transcribe / transcribe_batch call, summed over its audios
+    const whisper_b200_stats& last_stats() const { return last_stats_; }
 
 private:
     whisper_full_params make_params(const std::optional<std::string>& language, const std::string* initial_prompt, int beam_size) const;
     static std::optional<std::string> build_prompt(const std::optional<std::string>& vocabulary, const std::optional<std::string>& context);
+    void accumulate_stats(whisper_state* st, bool first) const;
     whisper_context* ctx_ = nullptr;
     std::string model_path_;
+    mutable whisper_b200_stats last_stats_{};
 };
 
 }  // namespace nobs

@@ -95,6 +95,34 @@ class WhisperEngine:
             self._raise(k)
         return [(t or b"").decode("utf-8", errors="replace") for t in texts]
 
+    def last_stats(self) -> "_lib.B200Stats":
+        s = _lib.B200Stats()
+        self._L.nobs_engine_last_stats(self._h, C.byref(s))
+        return s
+
+    def set_profiling(self, on: bool) -> None:
+        ctx = self._L.nobs_engine_context(self._h)
+        if ctx:
+            self._L.whisper_b200_set_profiling(ctx, int(on))
+
+    def event_record(self, slot: int) -> None:
+        """CUDA event on the library's stream (device-side timing of whole calls)."""
+        self._L.whisper_b200_event_record(self._L.nobs_engine_context(self._h), slot)
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        return self._L.whisper_b200_event_elapsed_ms(self._L.nobs_engine_context(self._h), a, b)
+
+    def transcribe_batch_ptrs(self, ptrs, lengths, language=None, vocabulary=None, beam_size: int = 0) -> list[str]:
+        """transcribe_batch over raw addresses (pinned host or device memory), e.g. torch tensors' data_ptr()."""
+        n = len(ptrs)
+        p = (C.POINTER(C.c_float) * n)(*[C.cast(C.c_void_p(int(a)), C.POINTER(C.c_float)) for a in ptrs])
+        ns = (C.c_int * n)(*[int(x) for x in lengths])
+        texts = (C.c_char_p * n)()
+        k = self._L.nobs_engine_transcribe_batch(self._h, p, ns, n, self._s(language), self._s(vocabulary), int(beam_size), texts)
+        if k:
+            self._raise(k)
+        return [(t or b"").decode("utf-8", errors="replace") for t in texts]
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.nobs_engine_free(self._h)

@@ -51,6 +51,7 @@ def _a(name, nv, d, h, le, ld, mels):
 # test-only architecture (same structure, d_head 64) small enough for second-scale CPU runs.
 ARCHS = {
     "micro": _a("micro", 51865, 128, 2, 2, 3, 80),  # 3 decoder layers: 2 would trip the distil rule
+    "micro128": _a("micro128", 51866, 128, 2, 2, 3, 128),  # test-only: v3 vocabulary layout + 128 mel bins
     "tiny": _a("tiny", 51865, 384, 6, 4, 4, 80),
     "base": _a("base", 51865, 512, 8, 6, 6, 80),
     "small": _a("small", 51865, 768, 12, 12, 12, 80),

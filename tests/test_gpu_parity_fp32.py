@@ -53,6 +53,14 @@ def ref_params(nw, language="en", prompt=None, beam=0, temperature_inc=None):
     return p
 
 
+def _compare_segments(got, want):
+    assert len(got) == len(want), (got, want)
+    for g, w in zip(got, want):
+        assert g["tokens"] == w["tokens"]      # token-exact
+        assert g["text"] == w["text"]
+        assert (g["t0"], g["t1"]) == (w["t0"], w["t1"])
+
+
 @pytest.mark.parametrize("seconds", [30.0, 5.0, 0.37, 47.3])
 def test_mel_parity(env, seconds):
     ctx, orc = env.get("micro")
@@ -67,9 +75,25 @@ def test_mel_parity(env, seconds):
     st.close()
 
 
-def test_mel_parity_128_bins(env):
-    ctx, orc = env.get("large-v3-turbo") if False else env.get("micro")
-    # 128-bin filterbank is covered on the real architecture in the bf16 tests; here: silence + clipping edge cases
+def test_v3_layout_128_mel_bins(env):
+    """large-v3 family specifics on a small model: 128-bin filterbank, 51866-token vocabulary
+    (special tokens shifted by one)."""
+    ctx, orc = env.get("micro128", "fanin")
+    assert ctx.n_mels() == 128 and ctx.n_vocab() == 51866 and ctx.token_beg() == 50365 == orc.token_beg
+    pcm = env.synth.synth_clip(31, 14.0)
+    st = ctx.create_state()
+    st.pcm_to_mel(pcm)
+    want, _ = orc.mel(pcm)
+    assert rel_err(st.get_mel(), want) < 1e-4
+    st.encode(0)
+    assert rel_err(st.encoder_output(), orc.encode(0)) < 1e-4
+    st.full(ref_params(env.nw), pcm)
+    _compare_segments(st.segments(), orc.full(env.oracle.reference_params("en"), pcm))
+    st.close()
+
+
+def test_mel_edge_signals(env):
+    ctx, orc = env.get("micro")
     for pcm in (np.zeros(16000 * 3, np.float32), np.ones(16000 * 2, np.float32), -np.ones(7777, np.float32)):
         st = ctx.create_state()
         st.pcm_to_mel(pcm)
@@ -149,14 +173,6 @@ def test_logit_filter_and_sampling_parity(env, temperature, mode):
         raw = logits.astype(np.float64)
         nosp = np.exp(raw[ctx.token_nosp()] - raw.max()) / np.exp(raw - raw.max()).sum()
         assert abs(res.no_speech_prob - nosp) < 1e-6
-
-
-def _compare_segments(got, want):
-    assert len(got) == len(want), (got, want)
-    for g, w in zip(got, want):
-        assert g["tokens"] == w["tokens"]      # token-exact
-        assert g["text"] == w["text"]
-        assert (g["t0"], g["t1"]) == (w["t0"], w["t1"])
 
 
 @pytest.mark.parametrize("arch,init,clip,seconds", [
