@@ -340,6 +340,10 @@ int whisper_b200_get_stats(struct whisper_state* state, whisper_b200_stats* out)
 int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const float* A, size_t a_elems, const float* W, const float* bias, int act,
                                  const float* res, int res_mod, int win_rows, int valid_rows, int out_f32, float* C_out);
 
+/* Kernel-level test hook: encoder self-attention (non-causal, 1500 valid keys of 1536 rows per window,
+ * head size 64).  qkv: [n_win*1536][3*64*n_head] fp32 (q|k|v), out: [n_win*1536][64*n_head] fp32. */
+int whisper_b200_debug_enc_attention(int n_win, int n_head, const float* qkv, float* out, int use_simt);
+
 /* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */
 int whisper_b200_event_record(struct whisper_context* ctx, int slot);
 double whisper_b200_event_elapsed_ms(struct whisper_context* ctx, int slot_a, int slot_b);

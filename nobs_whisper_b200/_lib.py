@@ -189,6 +189,7 @@ SIGNATURES = {
     "whisper_b200_debug_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int,
                                                C.c_int, fp]),
     "whisper_b200_set_profiling": (None, [vp, C.c_int]),
+    "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
     "whisper_b200_event_record": (C.c_int, [vp, C.c_int]),
     "whisper_b200_event_elapsed_ms": (C.c_double, [vp, C.c_int, C.c_int]),
     "whisper_b200_device_count": (C.c_int, []),

@@ -57,3 +57,27 @@ extern "C" int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const 
     }
     return 0;
 }
+
+// Encoder attention test hook: qkv fp32 host [n_win*1536][3*d] (q|k|v, rounded to bf16 on the device),
+// out fp32 host [n_win*1536][d].  use_simt != 0 runs the CUDA-core kernel instead of the tcgen05 one.
+extern "C" int whisper_b200_debug_enc_attention(int n_win, int n_head, const float* qkv, float* out, int use_simt) {
+    if (n_win <= 0 || n_head <= 0 || !qkv || !out) return -1;
+    const int d = n_head * 64;
+    const size_t rows = (size_t)n_win * kWinRows, in_elems = rows * 3 * d, out_elems = rows * d;
+    DevBuf dInF, dIn, dOut, dOutF;
+    if (!dInF.alloc(in_elems * 4) || !dIn.alloc(in_elems * 2) || !dOut.alloc(out_elems * 2) || !dOutF.alloc(out_elems * 4)) return -2;
+    cudaStream_t s = nullptr;
+    cudaMemcpy(dInF.p, qkv, in_elems * 4, cudaMemcpyHostToDevice);
+    launch_convert<float, bf16>((const float*)dInF.p, (bf16*)dIn.p, in_elems, s);
+    cudaMemset(dOut.p, 0, out_elems * 2);
+    if (use_simt) launch_enc_attention_simt<bf16>((const bf16*)dIn.p, (bf16*)dOut.p, n_win, n_head, d, s);
+    else if (!launch_enc_attention_bf16_sm100((const bf16*)dIn.p, (bf16*)dOut.p, n_win, n_head, d, s)) {
+        set_last_error(std::string("debug_enc_attention: ") + sm100_last_error());
+        return -3;
+    }
+    launch_convert<bf16, float>((const bf16*)dOut.p, (float*)dOutF.p, out_elems, s);
+    cudaMemcpyAsync(out, dOutF.p, out_elems * 4, cudaMemcpyDeviceToHost, s);
+    const cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) { set_last_error(std::string("debug_enc_attention: ") + cudaGetErrorString(err)); return -4; }
+    return 0;
+}

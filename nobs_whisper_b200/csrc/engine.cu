@@ -290,7 +290,8 @@ public:
                                     (size_t)run * kWinRows * d * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
             Epilogue e;
             e.bias = cross_b_;
-            if (!gemm(e_y_ + (size_t)w * kWinRows * d, d, cross_w_, d, cross_pool_ + (size_t)s0 * kWinRows * ldx, ldx, run * kWinRows, ldx, d, e, stream_))
+            e.head_rows = kWinRows;  // head-major panels [slot][(layer, K|V, head)][1536][64]: contiguous key streams for the decoder
+            if (!tgemm(e_y_ + (size_t)w * kWinRows * d, d, cross_w_, d, cross_pool_ + (size_t)s0 * kWinRows * ldx, ldx, run * kWinRows, ldx, d, e))
                 return gemm_fail();
             w += run;
         }
@@ -354,24 +355,25 @@ public:
         SampleResult* dres = reinterpret_cast<SampleResult*>(dev_scratch_ + rows_bytes + idx_bytes + sp_bytes);
 
         launch_embed<T>(drows, R, tok_emb_, dec_pos_, d_x_, d, stream_);
-        const size_t self_layer = (size_t)2 * ntc * d;             // [K|V][448][d]
-        const size_t self_slot = (size_t)Ld * self_layer;
-        const size_t cross_pos = (size_t)2 * Ld * d;               // position stride in the cross pool
-        const size_t cross_slot = (size_t)kWinRows * cross_pos;
+        // head-major KV panels: self [slot][layer][K|V][head][448][64], cross [slot][layer][K|V][head][1536][64]
+        const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
+        const size_t self_slot = (size_t)Ld * 2 * self_kv;
+        const size_t cross_head = (size_t)kWinRows * 64, cross_kv = (size_t)kWinRows * d;
+        const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
         for (int l = 0; l < Ld; ++l) {
             const Layer<T>& L = dec_[l];
             launch_layernorm<T>(d_x_, d, L.ln1_g, L.ln1_b, d_y_, d, R, d, stream_);
             { Epilogue e; e.bias = L.bqkv; if (!gemm(d_y_, d, L.wqkv, d, d_qkv_, 3 * d, R, 3 * d, d, e, stream_)) return gemm_fail(); }
-            T* kc = self_pool_ + (size_t)l * self_layer;
-            T* vc = kc + (size_t)ntc * d;
-            launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, d, stream_);
-            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, (size_t)d, 0, stream_);
+            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+            T* vc = kc + self_kv;
+            launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, ntc, d, stream_);
+            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
             { Epilogue e; e.bias = L.bo; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wo, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
             launch_layernorm<T>(d_x_, d, L.lnc_g, L.lnc_b, d_y_, d, R, d, stream_);
             { Epilogue e; e.bias = L.bcq; if (!gemm(d_y_, d, L.wcq, d, d_qkv_, d, R, d, d, e, stream_)) return gemm_fail(); }
-            const T* ck = cross_pool_ + (size_t)l * 2 * d;
-            const T* cv = ck + d;
-            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_pos, hp_.n_audio_ctx, stream_);
+            const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
+            const T* cv = ck + cross_kv;
+            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
             { Epilogue e; e.bias = L.bco; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wco, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
             launch_layernorm<T>(d_x_, d, L.ln2_g, L.ln2_b, d_y_, d, R, d, stream_);
             { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(d_y_, d, L.w1, d, d_h_, 4 * d, R, 4 * d, d, e, stream_)) return gemm_fail(); }
@@ -416,8 +418,8 @@ public:
         memcpy(pin_, pairs.data(), bytes);
         CUDA_OK(cudaMemcpyAsync(dev_scratch_, pin_, bytes, cudaMemcpyHostToDevice, stream_));
         const int d = d_, ntc = hp_.n_text_ctx, Ld = hp_.n_text_layer;
-        launch_kv_copy<T>(reinterpret_cast<const KvCopy*>(dev_scratch_), (int)pairs.size(), self_pool_, (size_t)Ld * 2 * ntc * d, 2 * Ld,
-                          (size_t)ntc * d, d, stream_);
+        launch_kv_copy<T>(reinterpret_cast<const KvCopy*>(dev_scratch_), (int)pairs.size(), self_pool_, (size_t)Ld * 2 * ntc * d,
+                          2 * Ld * hp_.n_text_head, (size_t)ntc * 64, stream_);
         CUDA_OK(cudaStreamSynchronize(stream_));
         return true;
     }
@@ -487,11 +489,14 @@ public:
         const size_t ldx = (size_t)2 * hp_.n_text_layer * d_;
         const size_t bytes = (size_t)n * d_ * sizeof(float);
         if (!ensure_dev_scratch(2 * bytes)) return false;
-        const T* base = cross_pool_ + (size_t)slot * kWinRows * ldx + (size_t)layer * 2 * d_;
+        const size_t cross_kv = (size_t)kWinRows * d_;
+        const T* base = cross_pool_ + (size_t)slot * kWinRows * ldx + (size_t)layer * 2 * cross_kv;
         float* dk = reinterpret_cast<float*>(dev_scratch_);
         float* dv = reinterpret_cast<float*>(dev_scratch_ + bytes);
-        launch_convert_2d<T, float>(base, ldx, dk, d_, n, d_, stream_);
-        launch_convert_2d<T, float>(base + d_, ldx, dv, d_, n, d_, stream_);
+        for (int h = 0; h < hp_.n_text_head; ++h) {  // head-major panels -> [pos][d]
+            launch_convert_2d<T, float>(base + (size_t)h * kWinRows * 64, 64, dk + h * 64, d_, n, 64, stream_);
+            launch_convert_2d<T, float>(base + cross_kv + (size_t)h * kWinRows * 64, 64, dv + h * 64, d_, n, 64, stream_);
+        }
         CUDA_OK(cudaMemcpyAsync(k, dk, bytes, cudaMemcpyDeviceToHost, stream_));
         CUDA_OK(cudaMemcpyAsync(v, dv, bytes, cudaMemcpyDeviceToHost, stream_));
         CUDA_OK(cudaStreamSynchronize(stream_));

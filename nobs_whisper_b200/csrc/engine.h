@@ -6,8 +6,9 @@
 //   weights        one arena; per layer Wqkv [3d,d] (q|k|v fused, K has no bias), Wo [d,d],
 //                  W1 [4d,d], W2 [d,4d]; conv weights re-ordered to [d][(tap, channel)];
 //                  all decoder layers' cross K/V projections fused into one [2*L*d, d] matrix.
-//   cross-KV pool  [audio_slot][1536 positions][L][K|V][d]  (written by ONE GEMM per encode batch)
-//   self-KV pool   [kv_slot][L][K|V][448 positions][d]
+//   cross-KV pool  [audio_slot][L][K|V][head][1536 positions][64]  (written by ONE GEMM per encode batch
+//                  through a head-major epilogue: each head's keys are one contiguous stream)
+//   self-KV pool   [kv_slot][L][K|V][head][448 positions][64]
 //   encoder out    [audio_slot][1536][d]
 //   activations    encoder: rows = windows x 1536 (1500 valid), decoder: rows = token rows.
 #pragma once

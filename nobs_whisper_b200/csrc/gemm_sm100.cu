@@ -20,6 +20,7 @@
 #include <string>
 
 #include "device_utils.cuh"
+#include "sm100_ptx.cuh"
 
 namespace nobs {
 
@@ -32,90 +33,6 @@ constexpr int BK = 64;       // one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// A protocol error must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-          "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled shared-memory operand: 8-row atoms of 1024 B (SBO), LBO unused (1),
-// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N x 128
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -214,7 +131,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     const uint32_t a_addr = smem_u32(sA + stage * A_BYTES), b_addr = smem_u32(sB + stage * cfg::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                        umma_bf16(tmem_d, make_smem_desc_kmajor(a_addr + k * UMMA_K * 2), make_smem_desc_kmajor(b_addr + k * UMMA_K * 2), idesc,
                                   (uint32_t)((kb | k) != 0));
                     umma_commit(&empty[stage]);                    // smem slot is free once these MMAs retire
                     if (kb == num_k - 1) umma_commit(&tfull[acc]);  // accumulator complete
@@ -239,6 +156,13 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const float* res_row = nullptr;
             if (e.res && row_ok) res_row = e.res + (size_t)(e.res_mod > 0 ? m % e.res_mod : m) * e.res_ld;
             TC* c_row = C + (size_t)m * ldc;
+            size_t head_base = 0;
+            int head_pos = 0;
+            if (e.head_rows > 0) {  // head-major (KV-cache) output layout
+                const int w = m / e.head_rows;
+                head_pos = m - w * e.head_rows;
+                head_base = (size_t)w * e.head_rows * ldc;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -258,12 +182,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         }
                         o[j] = row_zero ? 0.0f : x;
                     }
+                    // 32 consecutive columns never straddle a 64-wide head block (n0 % 32 == 0)
+                    TC* dst = e.head_rows > 0 ? C + head_base + ((size_t)(n0 >> 6) * e.head_rows + head_pos) * 64 + (n0 & 63) : c_row + n0;
                     if (vec_ok && n0 + 32 <= N) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) OutVec<TC>::store8(c_row + n0 + j, o + j);
+                        for (int j = 0; j < 32; j += 8) OutVec<TC>::store8(dst + j, o + j);
                     } else {
                         for (int j = 0; j < 32; ++j)
-                            if (n0 + j < N) c_row[n0 + j] = from_f32<TC>(o[j]);
+                            if (n0 + j < N) dst[j] = from_f32<TC>(o[j]);
                     }
                 }
             }
@@ -297,14 +223,20 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D bf16 tensor [rows][inner] with an arbitrary (16-byte multiple) row stride; box = 64 x box_rows, 128B swizzle
-bool make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+}  // namespace
+
+void sm100_set_error(const std::string& e) { g_err = e; }
+
+// 2D bf16 tensor [rows][inner] with an arbitrary (16-byte multiple) row stride — smaller than the row
+// length for the overlapping-row views; box = box_inner x box_rows, 128B swizzle, OOB reads as zero
+bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_inner,
+                       uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { g_err = "cuTensorMapEncodeTiled is not available"; return false; }
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * 2) % 16) { g_err = "TMA operand is not 16-byte aligned"; return false; }
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t strides[1] = {row_stride_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -315,6 +247,8 @@ bool make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows,
     }
     return true;
 }
+
+namespace {
 
 int num_sms() {
     static int n = 0;
@@ -331,8 +265,8 @@ template <int BN, typename TC>
 bool launch_cfg(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
     using cfg = Cfg<BN>;
     CUtensorMap ta, tb;
-    if (!make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM)) return false;
-    if (!make_tmap(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN)) return false;
+    if (!make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return false;
+    if (!make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN)) return false;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES) != cudaSuccess) {
@@ -371,11 +305,6 @@ bool launch_gemm_bf16_sm100(const bf16* A, int lda, const bf16* W, int ldw, void
     if (M <= 0 || N <= 0 || K <= 0) return true;
     if (c_is_f32) return dispatch<float>(A, lda, W, ldw, static_cast<float*>(C), ldc, M, N, K, e, s);
     return dispatch<bf16>(A, lda, W, ldw, static_cast<bf16*>(C), ldc, M, N, K, e, s);
-}
-
-bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s) {
-    launch_enc_attention_simt<bf16>(qkv, out, n_win, n_head, d, s);
-    return true;
 }
 
 const char* sm100_last_error() { return g_err.c_str(); }

@@ -236,7 +236,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = n0 + tx * 8 + j;
-            if (n < N) C[(size_t)m * ldc + n] = apply_epilogue(acc[i][j], m, n, e);
+            if (n < N) {
+                size_t idx = (size_t)m * ldc + n;
+                if (e.head_rows > 0) {
+                    const int w = m / e.head_rows, pos = m - w * e.head_rows;
+                    idx = (size_t)w * e.head_rows * ldc + ((size_t)(n >> 6) * e.head_rows + pos) * 64 + (n & 63);
+                }
+                C[idx] = apply_epilogue(acc[i][j], m, n, e);
+            }
         }
     }
 }
@@ -470,24 +477,26 @@ template void launch_embed<bf16>(const RowDesc*, int, const bf16*, const float*,
 
 template <typename T>
 __global__ void scatter_kv_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
-                                  size_t slot_stride, int d) {
+                                  size_t slot_stride, int n_pos_cap, int d) {
     const int r = blockIdx.x;
     const RowDesc rd = rows[r];
     const T* src = qkv + (size_t)r * 3 * d;
-    const size_t dst = (size_t)rd.kv_slot * slot_stride + (size_t)rd.pos * d;
+    const size_t base = (size_t)rd.kv_slot * slot_stride + (size_t)rd.pos * 64;
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        kc[dst + i] = src[d + i];
-        vc[dst + i] = src[2 * d + i];
+        const size_t dst = base + (size_t)(i >> 6) * n_pos_cap * 64 + (i & 63);
+        kc[dst] = src[d + i];
+        vc[dst] = src[2 * d + i];
     }
 }
 template <typename T>
-void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kcache, T* vcache, size_t slot_stride, int d, cudaStream_t s) {
+void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kpanel0, T* vpanel0, size_t slot_stride, int n_pos_cap, int d,
+                       cudaStream_t s) {
     if (n_rows <= 0) return;
-    scatter_kv_kernel<T><<<n_rows, 128, 0, s>>>(rows, qkv, kcache, vcache, slot_stride, d);
+    scatter_kv_kernel<T><<<n_rows, 128, 0, s>>>(rows, qkv, kpanel0, vpanel0, slot_stride, n_pos_cap, d);
     NOBS_COUNT_LAUNCH();
 }
-template void launch_scatter_kv<float>(const RowDesc*, int, const float*, float*, float*, size_t, int, cudaStream_t);
-template void launch_scatter_kv<bf16>(const RowDesc*, int, const bf16*, bf16*, bf16*, size_t, int, cudaStream_t);
+template void launch_scatter_kv<float>(const RowDesc*, int, const float*, float*, float*, size_t, int, int, cudaStream_t);
+template void launch_scatter_kv<bf16>(const RowDesc*, int, const bf16*, bf16*, bf16*, size_t, int, int, cudaStream_t);
 
 // dot of a 64-wide fp32 query (shared memory) with one K row
 __device__ __forceinline__ float dot64(const float* __restrict__ q, const float* __restrict__ k) {
@@ -521,7 +530,7 @@ __device__ __forceinline__ float dot64(const float* __restrict__ q, const bf16* 
 template <typename T>
 __global__ void __launch_bounds__(256) dec_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
                                                             const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
-                                                            int cross, size_t slot_stride, size_t key_stride, int n_keys) {
+                                                            int cross, size_t slot_stride, size_t head_stride, int n_keys) {
     __shared__ __align__(16) float qs[64];
     __shared__ float sc[kWinRows];
     __shared__ float red[32];
@@ -529,7 +538,8 @@ __global__ void __launch_bounds__(256) dec_attention_kernel(const RowDesc* __res
     const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const RowDesc rd = rows[r];
     const int nk = cross ? n_keys : rd.pos + 1;
-    const size_t base = (size_t)(cross ? rd.audio_slot : rd.kv_slot) * slot_stride + (size_t)h * 64;
+    const size_t base = (size_t)(cross ? rd.audio_slot : rd.kv_slot) * slot_stride + (size_t)h * head_stride;
+    constexpr size_t key_stride = 64;  // head-major panels: one key = 64 contiguous elements
     const T* K = kc + base;
     const T* V = vc + base;
     if (tid < 64) qs[tid] = to_f32(q[(size_t)r * ldq + h * 64 + tid]);
@@ -561,10 +571,10 @@ __global__ void __launch_bounds__(256) dec_attention_kernel(const RowDesc* __res
 }
 template <typename T>
 void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
-                          int cross, size_t slot_stride, size_t key_stride, int n_keys, cudaStream_t s) {
+                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s) {
     if (n_rows <= 0) return;
     dim3 grid(n_rows, n_head);
-    dec_attention_kernel<T><<<grid, 256, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, key_stride, n_keys);
+    dec_attention_kernel<T><<<grid, 256, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, head_stride, n_keys);
     NOBS_COUNT_LAUNCH();
 }
 template void launch_dec_attention<float>(const RowDesc*, int, const float*, int, const float*, const float*, float*, int, int, int, size_t, size_t,
@@ -572,24 +582,24 @@ template void launch_dec_attention<float>(const RowDesc*, int, const float*, int
 template void launch_dec_attention<bf16>(const RowDesc*, int, const bf16*, int, const bf16*, const bf16*, bf16*, int, int, int, size_t, size_t, int,
                                          cudaStream_t);
 
-// beam search: copy the first n_pos positions of every (layer, K|V) block of one self-KV slot to another
+// beam search: copy the first n_pos rows of every [n_pos_cap][64] panel of one self-KV slot to another
 template <typename T>
-__global__ void kv_copy_kernel(const KvCopy* __restrict__ pairs, T* __restrict__ pool, size_t slot_stride, size_t block_stride, int d) {
+__global__ void kv_copy_kernel(const KvCopy* __restrict__ pairs, T* __restrict__ pool, size_t slot_stride, size_t panel_stride) {
     const KvCopy p = pairs[blockIdx.x];
-    const size_t n = (size_t)p.n_pos * d;
-    const T* src = pool + (size_t)p.src * slot_stride + (size_t)blockIdx.y * block_stride;
-    T* dst = pool + (size_t)p.dst * slot_stride + (size_t)blockIdx.y * block_stride;
+    const size_t n = (size_t)p.n_pos * 64;
+    const T* src = pool + (size_t)p.src * slot_stride + (size_t)blockIdx.y * panel_stride;
+    T* dst = pool + (size_t)p.dst * slot_stride + (size_t)blockIdx.y * panel_stride;
     for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 template <typename T>
-void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_blocks, size_t block_stride, int d, cudaStream_t s) {
+void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_panels, size_t panel_stride, cudaStream_t s) {
     if (n_pairs <= 0) return;
-    dim3 grid(n_pairs, n_blocks);
-    kv_copy_kernel<T><<<grid, 256, 0, s>>>(pairs, pool, slot_stride, block_stride, d);
+    dim3 grid(n_pairs, n_panels);
+    kv_copy_kernel<T><<<grid, 128, 0, s>>>(pairs, pool, slot_stride, panel_stride);
     NOBS_COUNT_LAUNCH();
 }
-template void launch_kv_copy<float>(const KvCopy*, int, float*, size_t, int, size_t, int, cudaStream_t);
-template void launch_kv_copy<bf16>(const KvCopy*, int, bf16*, size_t, int, size_t, int, cudaStream_t);
+template void launch_kv_copy<float>(const KvCopy*, int, float*, size_t, int, size_t, cudaStream_t);
+template void launch_kv_copy<bf16>(const KvCopy*, int, bf16*, size_t, int, size_t, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // K6: logit filter + log-softmax + timestamp rule + argmax / sample / top-k, one block per row.

@@ -57,6 +57,10 @@ struct Epilogue {
     int res_mod = 0;
     int win_rows = 0;             // if > 0: rows with (m % win_rows) >= valid_rows are written as 0
     int valid_rows = 0;
+    // if > 0: head-major output.  Row m = (w, pos) with pos = m % head_rows; column n = 64*blk + e.
+    // Element goes to C[w*head_rows*ldc + (blk*head_rows + pos)*64 + e]: every 64-wide column block
+    // (one attention head of K or V) becomes a contiguous [head_rows][64] panel (KV-cache layout).
+    int head_rows = 0;
 };
 
 // C[M,N] = epi(A[M,K] * W[N,K]^T), all fp32, K-contiguous operands (fp32 parity mode)
@@ -86,20 +90,22 @@ struct RowDesc {
 };
 template <typename T>
 void launch_embed(const RowDesc* rows, int n_rows, const T* tok_emb, const float* pos_emb, float* x, int d, cudaStream_t s);
-// qkv [n_rows][3d] (q|k|v) -> K/V blocks of one layer: dst = block + kv_slot*slot_stride + pos*d
+// qkv [n_rows][3d] (q|k|v) -> head-major K/V panels of one layer:
+// dst = panel0 + kv_slot*slot_stride + (head*n_pos_cap + pos)*64 + e
 template <typename T>
-void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kblock, T* vblock, size_t slot_stride, int d, cudaStream_t s);
-// one (row, head) per block; key j of the row lives at base + slot*slot_stride + j*key_stride + head*64.
+void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kpanel0, T* vpanel0, size_t slot_stride, int n_pos_cap, int d,
+                       cudaStream_t s);
+// one (row, head) per block; key j of head h lives at base + slot*slot_stride + h*head_stride + j*64.
 // cross == 0: slot = kv_slot, keys 0..pos (causal);  cross == 1: slot = audio_slot, keys 0..n_keys-1.
 template <typename T>
 void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
-                          int cross, size_t slot_stride, size_t key_stride, int n_keys, cudaStream_t s);
-// self-KV slot copy for beam search: positions [0, n_pos) of each of the n_blocks (layer, K|V) blocks
+                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s);
+// self-KV slot copy for beam search: the first n_pos rows of each of the n_panels [n_pos_cap][64] panels
 struct KvCopy {
     int src, dst, n_pos;
 };
 template <typename T>
-void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_blocks, size_t block_stride, int d, cudaStream_t s);
+void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_panels, size_t panel_stride, cudaStream_t s);
 
 // ---------------------------------------------------------------- K6 logits -> token
 struct VocabIds {

@@ -75,3 +75,32 @@ def test_gemm_overlapping_rows_like_the_stem_convolutions():
     assert np.abs(out - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
     out, ref = run_gemm(3072, 1280, 384, lda=128, out_f32=True, seed=7)
     assert np.abs(out - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n_win,n_head,use_simt", [(1, 1, 0), (2, 3, 0), (1, 2, 1)])
+def test_encoder_attention_kernel(n_win, n_head, use_simt):
+    """tcgen05 flash attention (and the CUDA-core variant) against a float64 softmax(QK^T/8)V."""
+    from nobs_whisper_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(n_win * 10 + n_head)
+    d = 64 * n_head
+    rows = n_win * 1536
+    qkv = rng.standard_normal((rows, 3 * d)).astype(np.float32)
+    qkv[:, :d] *= 1.5          # a softmax that is neither flat nor one-hot
+    out = np.zeros((rows, d), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    rc = L.whisper_b200_debug_enc_attention(n_win, n_head, fp(qkv), fp(out), use_simt)
+    assert rc == 0, (rc, L.whisper_b200_last_error())
+    qb = to_bf16(qkv).astype(np.float64)
+    for w in range(n_win):
+        blk = qb[w * 1536:(w + 1) * 1536]
+        for h in range(n_head):
+            q = blk[:, h * 64:(h + 1) * 64]
+            k = blk[:1500, d + h * 64: d + (h + 1) * 64]
+            v = blk[:1500, 2 * d + h * 64: 2 * d + (h + 1) * 64]
+            s = q @ k.T * 0.125
+            p = np.exp(s - s.max(axis=1, keepdims=True))
+            ref = (p / p.sum(axis=1, keepdims=True)) @ v
+            got = out[w * 1536:(w + 1) * 1536, h * 64:(h + 1) * 64]
+            assert np.abs(got[:1500] - ref[:1500]).max() < 2e-2 * max(1.0, np.abs(ref).max())
+            assert np.isfinite(got).all()
