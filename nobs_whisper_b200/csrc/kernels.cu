@@ -498,75 +498,123 @@ void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kpanel0
 template void launch_scatter_kv<float>(const RowDesc*, int, const float*, float*, float*, size_t, int, int, cudaStream_t);
 template void launch_scatter_kv<bf16>(const RowDesc*, int, const bf16*, bf16*, bf16*, size_t, int, int, cudaStream_t);
 
-// dot of a 64-wide fp32 query (shared memory) with one K row
-__device__ __forceinline__ float dot64(const float* __restrict__ q, const float* __restrict__ k) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(k) + i);
-        acc = fmaf(q[4 * i + 0], v.x, acc);
-        acc = fmaf(q[4 * i + 1], v.y, acc);
-        acc = fmaf(q[4 * i + 2], v.z, acc);
-        acc = fmaf(q[4 * i + 3], v.w, acc);
+// ---- decoder attention over a head-major KV panel: one (row, head) per block.
+// A key / value row is 64 contiguous elements; LPK = 64*sizeof(T)/16 lanes cooperate on one row with a
+// 16-byte load each, so a warp instruction reads 512 contiguous bytes and the whole panel is streamed
+// exactly once for the scores and once for P*V (HBM-bound: the cross-attention panels are the
+// dominant traffic of a decoder step).
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
     }
-    return acc;
-}
-__device__ __forceinline__ float dot64(const float* __restrict__ q, const bf16* __restrict__ k) {
-    float acc = 0.0f;
+};
+template <> struct Vec16<bf16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(k) + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            acc = fmaf(q[8 * i + 2 * j + 0], f.x, acc);
-            acc = fmaf(q[8 * i + 2 * j + 1], f.y, acc);
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
         }
     }
-    return acc;
-}
+};
+
+constexpr int DA_THREADS = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(256) dec_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
-                                                            const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
-                                                            int cross, size_t slot_stride, size_t head_stride, int n_keys) {
+__global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+                                                                   const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
+                                                                   int cross, size_t slot_stride, size_t head_stride, int n_keys) {
+    constexpr int VN = Vec16<T>::N;            // elements per 16-byte load
+    constexpr int LPK = 64 / VN;               // lanes per key row (8 for bf16, 16 for fp32)
+    constexpr int KPI = DA_THREADS / LPK;      // keys per block iteration (32 / 16)
     __shared__ __align__(16) float qs[64];
     __shared__ float sc[kWinRows];
     __shared__ float red[32];
-    __shared__ float part[4][64];
+    __shared__ float part[KPI][64 + 1];
     const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const RowDesc rd = rows[r];
     const int nk = cross ? n_keys : rd.pos + 1;
     const size_t base = (size_t)(cross ? rd.audio_slot : rd.kv_slot) * slot_stride + (size_t)h * head_stride;
-    constexpr size_t key_stride = 64;  // head-major panels: one key = 64 contiguous elements
     const T* K = kc + base;
     const T* V = vc + base;
     if (tid < 64) qs[tid] = to_f32(q[(size_t)r * ldq + h * 64 + tid]);
     __syncthreads();
+    const int sub = tid % LPK, ks = tid / LPK;
+    float qv[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) qv[i] = qs[sub * VN + i];
+
+    // scores: 4 keys per thread in flight
     float lmax = -INFINITY;
-    for (int j = tid; j < nk; j += 256) {
-        const float s = dot64(qs, K + (size_t)j * key_stride) * 0.125f;
-        sc[j] = s;
-        lmax = fmaxf(lmax, s);
+    for (int j0 = 0; j0 < nk; j0 += 4 * KPI) {
+        float kv[4][VN];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * KPI + ks;
+            if (j < nk) Vec16<T>::load(K + (size_t)j * 64 + sub * VN, kv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * KPI + ks;
+            float acc = 0.0f;
+            if (j < nk) {
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc = fmaf(qv[i], kv[u][i], acc);
+            }
+#pragma unroll
+            for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (j < nk) {
+                acc *= 0.125f;
+                if (sub == 0) sc[j] = acc;
+                lmax = fmaxf(lmax, acc);
+            }
+        }
     }
-    const float mx = block_reduce(lmax, -INFINITY, OpMax(), red);
+    const float mx = block_reduce(lmax, -INFINITY, OpMax(), red);  // its barriers also publish sc[]
     float lsum = 0.0f;
-    for (int j = tid; j < nk; j += 256) {
+    for (int j = tid; j < nk; j += DA_THREADS) {
         const float p = expf(sc[j] - mx);
         sc[j] = p;
         lsum += p;
     }
-    const float total = block_reduce(lsum, 0.0f, OpAddF(), red);  // includes the barrier that publishes sc[]
+    const float total = block_reduce(lsum, 0.0f, OpAddF(), red);
     const float inv = 1.0f / total;
-    const int g = tid >> 6, e = tid & 63;
-    float acc = 0.0f;
-    for (int j = g; j < nk; j += 4) acc = fmaf(sc[j], to_f32(V[(size_t)j * key_stride + e]), acc);
-    part[g][e] = acc;
+
+    // P * V with the same (key slot, 16-byte lane) mapping
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+    for (int j0 = 0; j0 < nk; j0 += 4 * KPI) {
+        float vv[4][VN];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * KPI + ks;
+            if (j < nk) Vec16<T>::load(V + (size_t)j * 64 + sub * VN, vv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * KPI + ks;
+            if (j < nk) {
+                const float p = sc[j];
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, vv[u][i], acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) part[ks][sub * VN + i] = acc[i];
     __syncthreads();
     if (tid < 64) {
-        const float o = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv;
-        out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o);
+        float o = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < KPI; ++k) o += part[k][tid];
+        out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o * inv);
     }
 }
 template <typename T>
@@ -574,7 +622,7 @@ void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, 
                           int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s) {
     if (n_rows <= 0) return;
     dim3 grid(n_rows, n_head);
-    dec_attention_kernel<T><<<grid, 256, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, head_stride, n_keys);
+    dec_attention_kernel<T><<<grid, DA_THREADS, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, head_stride, n_keys);
     NOBS_COUNT_LAUNCH();
 }
 template void launch_dec_attention<float>(const RowDesc*, int, const float*, int, const float*, const float*, float*, int, int, int, size_t, size_t,
