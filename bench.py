@@ -228,7 +228,7 @@ def main():
             step(tensors)
         barrier()
         torch.cuda.synchronize()
-        agg = {"launches": 0, "gemm_ms": 0.0, "gemm_n": 0, "attn_ms": 0.0, "attn_n": 0, "rows": 0, "samples": 0, "windows": 0, "fallbacks": 0,
+        agg = {"launches": 0, "gemm_ms": 0.0, "gemm_n": 0, "attn_ms": 0.0, "attn_n": 0, "cross_ms": 0.0, "cross_n": 0, "cross_bytes": 0.0, "rows": 0, "samples": 0, "windows": 0, "fallbacks": 0,
                "ms_mel": 0.0, "ms_enc": 0.0, "ms_dec": 0.0, "rounds": 0, "d2h": 0}
         t0 = time.perf_counter()
         eng.event_record(0)  # CUDA events on the stream the kernels are launched on
@@ -236,6 +236,7 @@ def main():
             texts, s = step(tensors)
             agg["launches"] += s.n_kernel_launches; agg["gemm_ms"] += s.gpu_ms_enc_gemm; agg["gemm_n"] += s.n_enc_gemm
             agg["attn_ms"] += s.gpu_ms_enc_attn; agg["attn_n"] += s.n_enc_attn; agg["rows"] += s.n_decode_rows
+            agg["cross_ms"] += s.gpu_ms_dec_cross; agg["cross_n"] += s.n_dec_cross; agg["cross_bytes"] += s.dec_cross_bytes
             agg["samples"] += s.n_sample_rows; agg["windows"] += s.n_windows; agg["fallbacks"] += s.n_fallbacks
             agg["ms_mel"] += s.gpu_ms_mel; agg["ms_enc"] += s.gpu_ms_encode; agg["ms_dec"] += s.gpu_ms_decode
             agg["rounds"] += s.n_decode_rounds
@@ -285,6 +286,26 @@ def main():
                                       f"whisper-rs CPU path in fp32, {cdt:.1f} s of CPU work"}
             orc.close()
         steps = args.steps
+        # Dominant kernel of the step: the decoder's cross-attention stream over the cross-KV panels
+        # (HBM-bound).  achieved = algorithmic K/V bytes of the timed launches / summed CUDA-event durations.
+        cross_s = agg_dev["cross_ms"] / 1e3
+        cross_gbs = agg_dev["cross_bytes"] / cross_s / 1e9 if cross_s > 0 else 0.0
+        roofline = {
+            "bound": "hbm", "kernel": "dec_attention_kernel<bf16> (decoder cross-attention over the head-major cross-KV panels)",
+            "achieved": cross_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cross_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
+            "traffic": None, "peak_source": peaks["source"] + " hbm_gbs", "launches": agg_dev["cross_n"],
+            "algorithmic_bytes_per_launch": agg_dev["cross_bytes"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
+            "avg_launch_us": 1e3 * agg_dev["cross_ms"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
+            "share_of_step": agg_dev["cross_ms"] / (1000.0 * dt_dev) if dt_dev else None,
+            "other_kernels": {
+                "gemm_bf16_sm100_kernel (encoder side: conv stem, QKV/out/MLP, cross-KV projection)": {
+                    "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                    "launches": agg_dev["gemm_n"], "share_of_step": agg_dev["gemm_ms"] / (1000.0 * dt_dev) if dt_dev else None},
+                "enc_attention_sm100_kernel": {
+                    "bound": "tensor", "achieved": attn_tf, "peak": peak, "unit": "TFLOP/s", "frac": attn_tf / peak if peak else None,
+                    "launches": agg_dev["attn_n"], "share_of_step": agg_dev["attn_ms"] / (1000.0 * dt_dev) if dt_dev else None},
+            },
+        }
         line = {
             "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -302,11 +323,7 @@ def main():
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int(agg_e2e["d2h"] / steps) * world,
                     "ms_per_step": 1000.0 * dt_e2e / steps},
             "gpu_launches": int(agg_dev["launches"] + agg_e2e["launches"]),
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_sm100_kernel (encoder-side GEMMs: conv stem, QKV/out/MLP, cross-KV)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
-                         "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": agg_dev["gemm_n"],
-                         "share_of_step": agg_dev["gemm_ms"] / (1000.0 * dt_dev) if dt_dev else None,
-                         "encoder_attention": {"achieved_tflops": attn_tf, "ms_per_step": agg_dev["attn_ms"] / steps, "launches": agg_dev["attn_n"]}},
+            "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }

@@ -329,6 +329,11 @@ typedef struct whisper_b200_stats {
      * GEMM kernel (conv stem, QKV/out/MLP, cross-KV projection) and of the encoder attention kernel */
     double gpu_ms_enc_gemm, gpu_ms_enc_attn;
     int64_t n_enc_gemm, n_enc_attn;
+    /* decoder cross-attention kernel (the HBM-bound stream over the cross-KV panels): summed per-launch
+     * durations, launches, and the algorithmic K/V bytes those launches had to read */
+    double gpu_ms_dec_cross;
+    int64_t n_dec_cross;
+    double dec_cross_bytes;
 } whisper_b200_stats;
 /* Record a CUDA-event pair around every encoder GEMM / attention launch (costs ~1 us per launch). */
 void whisper_b200_set_profiling(struct whisper_context* ctx, int on);
@@ -343,6 +348,10 @@ int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const float* A, s
 /* Kernel-level test hook: encoder self-attention (non-causal, 1500 valid keys of 1536 rows per window,
  * head size 64).  qkv: [n_win*1536][3*64*n_head] fp32 (q|k|v), out: [n_win*1536][64*n_head] fp32. */
 int whisper_b200_debug_enc_attention(int n_win, int n_head, const float* qkv, float* out, int use_simt);
+
+/* Micro-benchmark hook: average device microseconds per launch of the decoder-step kernels for R token
+ * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..10]). */
+int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us);
 
 /* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */
 int whisper_b200_event_record(struct whisper_context* ctx, int slot);

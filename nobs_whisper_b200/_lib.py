@@ -109,6 +109,7 @@ class B200Stats(C.Structure):
         ("n_sample_rows", C.c_int64), ("n_fallbacks", C.c_int64), ("n_kernel_launches", C.c_int64),
         ("gpu_ms_mel", C.c_double), ("gpu_ms_encode", C.c_double), ("gpu_ms_decode", C.c_double),
         ("gpu_ms_enc_gemm", C.c_double), ("gpu_ms_enc_attn", C.c_double), ("n_enc_gemm", C.c_int64), ("n_enc_attn", C.c_int64),
+        ("gpu_ms_dec_cross", C.c_double), ("n_dec_cross", C.c_int64), ("dec_cross_bytes", C.c_double),
     ]
 
 
@@ -190,6 +191,7 @@ SIGNATURES = {
                                                C.c_int, fp]),
     "whisper_b200_set_profiling": (None, [vp, C.c_int]),
     "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
+    "whisper_b200_debug_time_decode_kernels": (C.c_int, [C.c_int, C.c_int, C.c_int, fp]),
     "whisper_b200_event_record": (C.c_int, [vp, C.c_int]),
     "whisper_b200_event_elapsed_ms": (C.c_double, [vp, C.c_int, C.c_int]),
     "whisper_b200_device_count": (C.c_int, []),

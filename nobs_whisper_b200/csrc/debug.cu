@@ -1,5 +1,7 @@
 // Test hooks that run single kernels of the bf16 path on caller-supplied data (C ABI, used by
 // tests/test_gpu_kernels_bf16.py).  Not on any product path.
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -79,5 +81,105 @@ extern "C" int whisper_b200_debug_enc_attention(int n_win, int n_head, const flo
     cudaMemcpyAsync(out, dOutF.p, out_elems * 4, cudaMemcpyDeviceToHost, s);
     const cudaError_t err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) { set_last_error(std::string("debug_enc_attention: ") + cudaGetErrorString(err)); return -4; }
+    return 0;
+}
+
+// Micro-benchmark hook: average device time per launch (events around `iters` back-to-back launches) of
+// the decoder-step kernels at large-v3 dimensions for R token rows.  out_us[]: 0 skinny QKV (N=3d,K=d),
+// 1 skinny out (N=d,K=d), 2 skinny FC1 (N=4d,K=d), 3 skinny FC2 (N=d,K=4d), 4 reduce plain N=3d,
+// 5 reduce resid+LN N=d, 6 reduce gelu N=4d, 7 self-attention (100 keys), 8 cross-attention (1500 keys),
+// 9 generic GEMM N=d K=d (previous path), 10 layernorm.
+extern "C" int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us) {
+    if (R <= 0 || R > 128 || d % 64 || iters <= 0 || !out_us) return -1;
+    const int H = d / 64, ntc = 448;
+    DevBuf x, y, big, att, W, partial, bias, g, kv, ckv, rows;
+    const size_t wmax = (size_t)4 * d * d;
+    if (!x.alloc((size_t)128 * d * 4) || !y.alloc((size_t)128 * 4 * d * 2) || !big.alloc((size_t)128 * 4 * d * 2) || !att.alloc((size_t)128 * d * 2) ||
+        !W.alloc(wmax * 2) || !partial.alloc((size_t)16 << 20) || !bias.alloc((size_t)4 * d * 4) || !g.alloc((size_t)4 * d * 4) ||
+        !kv.alloc((size_t)R * 2 * ntc * d * 2) || !ckv.alloc((size_t)R * 2 * kWinRows * d * 2) || !rows.alloc(sizeof(RowDesc) * 128))
+        return -2;
+    cudaMemset(x.p, 0, (size_t)128 * d * 4); cudaMemset(y.p, 0, (size_t)128 * 4 * d * 2); cudaMemset(big.p, 0, (size_t)128 * 4 * d * 2);
+    cudaMemset(att.p, 0, (size_t)128 * d * 2); cudaMemset(W.p, 0, wmax * 2); cudaMemset(bias.p, 0, (size_t)4 * d * 4); cudaMemset(g.p, 0, (size_t)4 * d * 4);
+    cudaMemset(kv.p, 0, (size_t)R * 2 * ntc * d * 2); cudaMemset(ckv.p, 0, (size_t)R * 2 * kWinRows * d * 2);
+    std::vector<RowDesc> hr(128);
+    for (int i = 0; i < 128; ++i) hr[i] = RowDesc{1, 100, i % R, i % R};
+    cudaMemcpy(rows.p, hr.data(), sizeof(RowDesc) * 128, cudaMemcpyHostToDevice);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto timeit = [&](int idx, auto&& fn) {
+        for (int i = 0; i < 3; ++i) fn();
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i) fn();
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        out_us[idx] = 1e3f * ms / iters;
+    };
+    int splits = 0;
+    const bf16* X = (const bf16*)y.p;
+    const bf16* Wp = (const bf16*)W.p;
+    float* P = (float*)partial.p;
+    timeit(0, [&] { launch_gemm_skinny_bf16_sm100(X, d, Wp, d, P, R, 3 * d, d, &splits, s); });
+    timeit(1, [&] { launch_gemm_skinny_bf16_sm100(X, d, Wp, d, P, R, d, d, &splits, s); });
+    timeit(2, [&] { launch_gemm_skinny_bf16_sm100(X, d, Wp, d, P, R, 4 * d, d, &splits, s); });
+    timeit(3, [&] { launch_gemm_skinny_bf16_sm100(X, 4 * d, Wp, 4 * d, P, R, d, 4 * d, &splits, s); });
+    auto red = [&](int N, int K, bool resid, bool ln, int act) {
+        SkinnyEpilogue e;
+        e.partial = P; e.splits = skinny_gemm_splits(N, K); e.R = R; e.N = N; e.bias = (const float*)bias.p; e.act = act;
+        if (resid) e.x = (float*)x.p; else { e.out = big.p; e.out_ld = N; }
+        if (ln) { e.ln_g = (const float*)g.p; e.ln_b = (const float*)g.p; e.y = y.p; }
+        launch_skinny_reduce<bf16>(e, s);
+    };
+    timeit(4, [&] { red(3 * d, d, false, false, 0); });
+    timeit(5, [&] { red(d, d, true, true, 0); });
+    timeit(6, [&] { red(4 * d, d, false, false, 1); });
+    timeit(7, [&] { launch_dec_attention<bf16>((const RowDesc*)rows.p, R, (const bf16*)big.p, 3 * d, (const bf16*)kv.p, (const bf16*)kv.p + (size_t)ntc * d,
+                                               (bf16*)att.p, d, H, 0, (size_t)2 * ntc * d, (size_t)ntc * 64, 0, s); });
+    timeit(8, [&] { launch_dec_attention<bf16>((const RowDesc*)rows.p, R, (const bf16*)big.p, d, (const bf16*)ckv.p, (const bf16*)ckv.p + (size_t)kWinRows * d,
+                                               (bf16*)att.p, d, H, 1, (size_t)2 * kWinRows * d, (size_t)kWinRows * 64, 1500, s); });
+    timeit(9, [&] { Epilogue e; e.bias = (const float*)bias.p; launch_gemm_bf16_sm100(X, d, Wp, d, big.p, d, false, R, d, d, e, s); });
+    timeit(10, [&] { launch_layernorm<bf16>((const float*)x.p, d, (const float*)g.p, (const float*)g.p, (bf16*)y.p, d, R, d, s); });
+    // launch turnaround floor: the same tiny kernel chain (a) as stream launches, (b) as one CUDA graph
+    if (const char* g_env = getenv("NOBS_DEBUG_GRAPH")) {
+        (void)g_env;
+        auto chain = [&] {
+            for (int l = 0; l < 8; ++l) {
+                launch_gemm_skinny_bf16_sm100(X, d, Wp, d, P, R, d, d, &splits, s);
+                red(d, d, true, true, 0);
+                launch_layernorm<bf16>((const float*)x.p, d, (const float*)g.p, (const float*)g.p, (bf16*)y.p, d, R, d, s);
+            }
+        };
+        chain();
+        cudaStreamSynchronize(s);
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < 20; ++i) chain();
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[debug] stream chain: %.2f us per kernel\n", 1e3f * ms / (20 * 24));
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        chain();
+        cudaStreamEndCapture(s, &graph);
+        cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphLaunch(exec, s);
+        cudaStreamSynchronize(s);
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < 20; ++i) cudaGraphLaunch(exec, s);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[debug] graph chain:  %.2f us per kernel (err %s)\n", 1e3f * ms / (20 * 24), cudaGetErrorString(cudaGetLastError()));
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    }
+    const cudaError_t err = cudaStreamSynchronize(s);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+    if (err != cudaSuccess) { set_last_error(std::string("debug_time: ") + cudaGetErrorString(err)); return -4; }
     return 0;
 }

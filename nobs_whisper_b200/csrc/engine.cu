@@ -1,9 +1,11 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 
@@ -81,6 +83,13 @@ public:
         if (encout_pool_) cudaFree(encout_pool_);
         if (pcm_dev_) cudaFree(pcm_dev_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        if (env_int("NOBS_WHISPER_PROFILE_HOST", 0))
+            fprintf(stderr, "[nobs profile] decode host: issuing launches %.1f ms, waiting for the GPU %.1f ms\n", host_issue_ms_, host_wait_ms_);
+        if (detail_) {
+            const char* names[8] = {"skinny_gemm", "skinny_reduce", "self_attn", "cross_attn", "layernorm", "logits+sample", "embed", "other"};
+            for (int i = 0; i < 8; ++i)
+                if (detail_n_[i]) fprintf(stderr, "[nobs profile] %-14s n=%8ld total=%10.2f ms avg=%8.2f us\n", names[i], detail_n_[i], detail_ms_[i], 1e3 * detail_ms_[i] / detail_n_[i]);
+        }
         for (auto& e : ev_pool_) cudaEventDestroy(e);
         for (auto& e : user_ev_) if (e) cudaEventDestroy(e);
         if (stream_) cudaStreamDestroy(stream_);
@@ -220,12 +229,16 @@ public:
         marks_.push_back({cls, (int)ev_used_});
         ev_used_ += 2;
     }
+    void dmark_begin() { if (detail_) { const bool p = profiling; profiling = true; mark_begin(); profiling = p; } }
+    void dmark_end(int cls) { if (detail_) { const bool p = profiling; profiling = true; mark_end(cls); profiling = p; } }
     void collect_marks() {  // call after the stream has been synchronised
         for (const auto& m : marks_) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_pool_[m.second], ev_pool_[m.second + 1]);
-            if (m.first == 0) { stats.ms_enc_gemm += ms; stats.n_enc_gemm++; }
-            else { stats.ms_enc_attn += ms; stats.n_enc_attn++; }
+            if (m.first >= 10) { detail_ms_[m.first - 10] += ms; detail_n_[m.first - 10]++; }
+            else if (m.first == 0) { stats.ms_enc_gemm += ms; stats.n_enc_gemm++; }
+            else if (m.first == 1) { stats.ms_enc_attn += ms; stats.n_enc_attn++; }
+            else { stats.ms_dec_cross += ms; stats.n_dec_cross++; }
         }
         marks_.clear();
         ev_used_ = 0;
@@ -327,6 +340,80 @@ public:
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
         stats.ms_decode += ms;
+        collect_marks();
+        return true;
+    }
+
+    // Decoder layers for a step batch of R <= 128 token rows (bf16): every projection is a swap-AB split-K
+    // tcgen05 GEMM that streams its weights through all SMs, finished by one fused epilogue kernel
+    // (bias / GELU / residual / next LayerNorm / KV scatter).  14 launches per layer.
+    bool decode_layers_skinny(const RowDesc* drows, int R) {
+        const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
+        const size_t self_slot = (size_t)Ld * 2 * self_kv;
+        const size_t cross_head = (size_t)kWinRows * 64, cross_kv = (size_t)kWinRows * d;
+        const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
+        const bf16* y = reinterpret_cast<const bf16*>(d_y_);
+        auto proj = [&](const void* X, int K, const T* W, int N, SkinnyEpilogue& e) -> bool {
+            int splits = 0;
+            dmark_begin();
+            if (!launch_gemm_skinny_bf16_sm100(reinterpret_cast<const bf16*>(X), K, reinterpret_cast<const bf16*>(W), K, d_partial_, R, N, K, &splits,
+                                               stream_))
+                return gemm_fail();
+            dmark_end(10);
+            e.partial = d_partial_; e.splits = splits; e.R = R; e.N = N;
+            dmark_begin();
+            launch_skinny_reduce<T>(e, stream_);
+            dmark_end(11);
+            return true;
+        };
+        launch_layernorm<T>(d_x_, d, dec_[0].ln1_g, dec_[0].ln1_b, d_y_, d, R, d, stream_);
+        for (int l = 0; l < Ld; ++l) {
+            const Layer<T>& L = dec_[l];
+            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+            T* vc = kc + self_kv;
+            {   // QKV projection + KV-cache append
+                SkinnyEpilogue e;
+                e.bias = L.bqkv; e.out = d_qkv_; e.out_ld = 3 * d;
+                e.rows = drows; e.kpanel = kc; e.vpanel = vc; e.slot_stride = self_slot; e.n_pos_cap = ntc; e.d = d;
+                if (!proj(y, d, L.wqkv, 3 * d, e)) return false;
+            }
+            dmark_begin();
+            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
+            dmark_end(12);
+            {   // out projection + residual + cross-attention LayerNorm
+                SkinnyEpilogue e;
+                e.bias = L.bo; e.x = d_x_; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = d_y_;
+                if (!proj(d_att_, d, L.wo, d, e)) return false;
+            }
+            {   // cross-attention query
+                SkinnyEpilogue e;
+                e.bias = L.bcq; e.out = d_qkv_; e.out_ld = d;
+                if (!proj(y, d, L.wcq, d, e)) return false;
+            }
+            const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
+            const T* cv = ck + cross_kv;
+            const bool timed = profiling && (l % kCrossSample) == 0;
+            if (timed) mark_begin(); else dmark_begin();
+            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
+            if (timed) { mark_end(2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else dmark_end(13);
+            {   // cross out projection + residual + MLP LayerNorm
+                SkinnyEpilogue e;
+                e.bias = L.bco; e.x = d_x_; e.ln_g = L.ln2_g; e.ln_b = L.ln2_b; e.y = d_y_;
+                if (!proj(d_att_, d, L.wco, d, e)) return false;
+            }
+            {   // FC1 + GELU
+                SkinnyEpilogue e;
+                e.bias = L.b1; e.act = 1; e.out = d_h_; e.out_ld = 4 * d;
+                if (!proj(y, d, L.w1, 4 * d, e)) return false;
+            }
+            {   // FC2 + residual + the next layer's first LayerNorm
+                SkinnyEpilogue e;
+                e.bias = L.b2; e.x = d_x_;
+                if (l + 1 < Ld) { e.ln_g = dec_[l + 1].ln1_g; e.ln_b = dec_[l + 1].ln1_b; e.y = d_y_; }
+                if (!proj(d_h_, 4 * d, L.w2, d, e)) return false;
+            }
+        }
         return true;
     }
 
@@ -354,40 +441,55 @@ public:
         const SampleParams* dsp = reinterpret_cast<const SampleParams*>(dev_scratch_ + rows_bytes + idx_bytes);
         SampleResult* dres = reinterpret_cast<SampleResult*>(dev_scratch_ + rows_bytes + idx_bytes + sp_bytes);
 
+        const auto host_t0 = std::chrono::steady_clock::now();
         launch_embed<T>(drows, R, tok_emb_, dec_pos_, d_x_, d, stream_);
         // head-major KV panels: self [slot][layer][K|V][head][448][64], cross [slot][layer][K|V][head][1536][64]
         const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
         const size_t self_slot = (size_t)Ld * 2 * self_kv;
         const size_t cross_head = (size_t)kWinRows * 64, cross_kv = (size_t)kWinRows * d;
         const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
-        for (int l = 0; l < Ld; ++l) {
-            const Layer<T>& L = dec_[l];
-            launch_layernorm<T>(d_x_, d, L.ln1_g, L.ln1_b, d_y_, d, R, d, stream_);
-            { Epilogue e; e.bias = L.bqkv; if (!gemm(d_y_, d, L.wqkv, d, d_qkv_, 3 * d, R, 3 * d, d, e, stream_)) return gemm_fail(); }
-            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
-            T* vc = kc + self_kv;
-            launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, ntc, d, stream_);
-            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
-            { Epilogue e; e.bias = L.bo; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wo, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
-            launch_layernorm<T>(d_x_, d, L.lnc_g, L.lnc_b, d_y_, d, R, d, stream_);
-            { Epilogue e; e.bias = L.bcq; if (!gemm(d_y_, d, L.wcq, d, d_qkv_, d, R, d, d, e, stream_)) return gemm_fail(); }
-            const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
-            const T* cv = ck + cross_kv;
-            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
-            { Epilogue e; e.bias = L.bco; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wco, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
-            launch_layernorm<T>(d_x_, d, L.ln2_g, L.ln2_b, d_y_, d, R, d, stream_);
-            { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(d_y_, d, L.w1, d, d_h_, 4 * d, R, 4 * d, d, e, stream_)) return gemm_fail(); }
-            { Epilogue e; e.bias = L.b2; e.res = d_x_; e.res_ld = d; if (!gemm(d_h_, 4 * d, L.w2, 4 * d, d_x_, d, R, d, 4 * d, e, stream_)) return gemm_fail(); }
+        const bool skinny = use_skinny_ && sizeof(T) == 2 && R <= 128 && 4 * d <= 5120;
+        if (skinny) {
+            if (!decode_layers_skinny(drows, R)) return false;
+        } else {
+            for (int l = 0; l < Ld; ++l) {
+                const Layer<T>& L = dec_[l];
+                launch_layernorm<T>(d_x_, d, L.ln1_g, L.ln1_b, d_y_, d, R, d, stream_);
+                { Epilogue e; e.bias = L.bqkv; if (!gemm(d_y_, d, L.wqkv, d, d_qkv_, 3 * d, R, 3 * d, d, e, stream_)) return gemm_fail(); }
+                T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+                T* vc = kc + self_kv;
+                launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, ntc, d, stream_);
+                launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
+                { Epilogue e; e.bias = L.bo; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wo, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
+                launch_layernorm<T>(d_x_, d, L.lnc_g, L.lnc_b, d_y_, d, R, d, stream_);
+                { Epilogue e; e.bias = L.bcq; if (!gemm(d_y_, d, L.wcq, d, d_qkv_, d, R, d, d, e, stream_)) return gemm_fail(); }
+                const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
+                const T* cv = ck + cross_kv;
+                mark_begin();
+                launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
+                mark_end(2);
+                if (profiling) stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T);
+                { Epilogue e; e.bias = L.bco; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wco, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
+                launch_layernorm<T>(d_x_, d, L.ln2_g, L.ln2_b, d_y_, d, R, d, stream_);
+                { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(d_y_, d, L.w1, d, d_h_, 4 * d, R, 4 * d, d, e, stream_)) return gemm_fail(); }
+                { Epilogue e; e.bias = L.b2; e.res = d_x_; e.res_ld = d; if (!gemm(d_h_, 4 * d, L.w2, 4 * d, d_x_, d, R, d, 4 * d, e, stream_)) return gemm_fail(); }
+            }
         }
         if (S > 0) {
+            dmark_begin();
             launch_layernorm_gather<T>(d_x_, d, didx, dec_ln_g_, dec_ln_b_, d_ys_, d, S, d, stream_);
             { Epilogue e; if (!gemm(d_ys_, d, tok_emb_, d, d_logits_, hp_.n_vocab, S, hp_.n_vocab, d, e, stream_)) return gemm_fail(); }
             launch_process_logits(d_logits_, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, nullptr, stream_);
+            dmark_end(15);
             CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, stream_));
             if (logits_host)
                 CUDA_OK(cudaMemcpyAsync(logits_host, d_logits_, sizeof(float) * (size_t)S * hp_.n_vocab, cudaMemcpyDeviceToHost, stream_));
         }
+        const auto host_t1 = std::chrono::steady_clock::now();
         CUDA_OK(cudaStreamSynchronize(stream_));
+        const auto host_t2 = std::chrono::steady_clock::now();
+        host_issue_ms_ += std::chrono::duration<double, std::milli>(host_t1 - host_t0).count();
+        host_wait_ms_ += std::chrono::duration<double, std::milli>(host_t2 - host_t1).count();
         CUDA_OK(cudaGetLastError());
         if (S > 0) memcpy(res, hp + rows_bytes + idx_bytes + sp_bytes, sizeof(SampleResult) * S);
         last_logit_rows_ = S;
@@ -733,6 +835,8 @@ private:
         enc_batch_ = std::max(1, env_int("NOBS_WHISPER_ENC_BATCH", f32 ? 2 : 8));
         dec_rows_ = std::max(64, env_int("NOBS_WHISPER_DEC_ROWS", 4096));
         dec_samples_ = std::max(8, env_int("NOBS_WHISPER_DEC_SAMPLES", 1024));
+        use_skinny_ = env_int("NOBS_WHISPER_SKINNY", 1) != 0;
+        detail_ = env_int("NOBS_WHISPER_PROFILE_DECODE", 0) != 0;
         // encoder and decoder never run concurrently: both views alias one arena
         Arena e;
         auto plan_enc = [&](Arena& a) {
@@ -752,6 +856,7 @@ private:
             d_qkv_ = (T*)a.take(R * 3 * d * sizeof(T));
             d_att_ = (T*)a.take(R * d * sizeof(T));
             d_h_ = (T*)a.take(R * 4 * d * sizeof(T));
+            d_partial_ = (float*)a.take((size_t)16 << 20);  // skinny-GEMM split-K partials: <= 4 splits x 128 rows x 5120 cols (FC1) fp32
             d_ys_ = (T*)a.take(S * d * sizeof(T));
             d_logits_ = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
         };
@@ -816,6 +921,13 @@ private:
     float* d_x_ = nullptr;
     T *d_y_ = nullptr, *d_qkv_ = nullptr, *d_att_ = nullptr, *d_h_ = nullptr, *d_ys_ = nullptr;
     float* d_logits_ = nullptr;
+    float* d_partial_ = nullptr;
+    bool use_skinny_ = true;
+    bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
+    double host_issue_ms_ = 0, host_wait_ms_ = 0;  // decode_chunk: time spent issuing launches vs waiting for the GPU
+    double detail_ms_[8] = {};
+    long detail_n_[8] = {};
+    static constexpr int kCrossSample = 8;  // profiling: time the cross-attention of every 8th layer
     int last_logit_rows_ = 0;
 
     cudaEvent_t user_ev_[8] = {};

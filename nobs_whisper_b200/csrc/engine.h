@@ -51,8 +51,9 @@ struct EncodeRequest {
 struct EngineStats {
     double ms_mel = 0, ms_encode = 0, ms_decode = 0;
     // per-launch CUDA-event timing of the encoder's kernel classes (only when profiling is on)
-    double ms_enc_gemm = 0, ms_enc_attn = 0;
-    long n_enc_gemm = 0, n_enc_attn = 0;
+    double ms_enc_gemm = 0, ms_enc_attn = 0, ms_dec_cross = 0;
+    long n_enc_gemm = 0, n_enc_attn = 0, n_dec_cross = 0;
+    double dec_cross_bytes = 0;  // algorithmic K/V panel bytes read by the timed cross-attention launches
     long n_launches = 0;
 };
 

@@ -165,6 +165,9 @@ public:
             s.gpu_ms_enc_attn = eng_.stats.ms_enc_attn;
             s.n_enc_gemm = eng_.stats.n_enc_gemm;
             s.n_enc_attn = eng_.stats.n_enc_attn;
+            s.gpu_ms_dec_cross = eng_.stats.ms_dec_cross;
+            s.n_dec_cross = eng_.stats.n_dec_cross;
+            s.dec_cross_bytes = eng_.stats.dec_cross_bytes;
         }
         return 0;
     }

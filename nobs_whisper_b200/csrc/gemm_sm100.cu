@@ -16,6 +16,7 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -91,10 +92,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything above overlapped the previous kernel's tail
 
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
@@ -207,6 +210,126 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Skinny GEMM for decoder steps (R <= 128 token rows): swap-AB + split-K.
+//   D^T[n, r] = sum_k W[n, k] * X[r, k]   — the weight tile is the 128-row UMMA "A" operand, the R token
+//   rows are the (small) "B" operand, so a CTA streams 16 KB of weights per k-block and the activations
+//   ride along from L2.  The K range is split across CTAs so that every SM pulls weights from HBM
+//   (N_out/128 tiles alone would occupy 10-40 SMs); fp32 partial sums go to a workspace
+//   [split][R][N_out] and skinny_reduce_kernel (kernels.cu) sums them in a fixed order and applies
+//   bias / GELU / residual / LayerNorm / KV-cache scatter.
+constexpr int kSkinnyStages = 3;
+
+template <int BN>
+__global__ void __launch_bounds__(256, 2)
+gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ partial, int R,
+                         int N, int K, int kb_per_split) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGES = kSkinnyStages;   // a CTA only sees a few k-blocks: shallow ring, two CTAs fit per SM
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, split = blockIdx.y;
+    const int num_k = (K + BK - 1) / BK;
+    const int kb0 = split * kb_per_split, kb1 = min(num_k, kb0 + kb_per_split);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // The weights do not depend on the previous kernel: fill the ring with weight tiles first, and only
+        // then wait for the predecessor (PDL) before fetching the activations it produced.
+        const int pre = min(STAGES, kb1 - kb0);
+        if (lane == 0) {
+            for (int i = 0; i < pre; ++i) {
+                mbar_expect_tx(&full[i], STAGE_BYTES);
+                tma_load_2d(sA + i * A_BYTES, &tmap_w, &full[i], (kb0 + i) * BK, m_blk * BM);
+            }
+        }
+        pdl_wait();
+        if (lane == 0) {
+            for (int i = 0; i < pre; ++i) tma_load_2d(sB + i * B_BYTES, &tmap_x, &full[i], (kb0 + i) * BK, 0);
+        }
+        __syncwarp();
+        int stage = pre % STAGES; uint32_t phase = pre == STAGES ? 1 : 0;
+        for (int kb = kb0 + pre; kb < kb1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) {
+                mbar_expect_tx(&full[stage], STAGE_BYTES);
+                tma_load_2d(sA + stage * A_BYTES, &tmap_w, &full[stage], kb * BK, m_blk * BM);
+                tma_load_2d(sB + stage * B_BYTES, &tmap_x, &full[stage], kb * BK, 0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BN);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sA + stage * A_BYTES), b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_smem_desc_kmajor(a_addr + k * UMMA_K * 2), make_smem_desc_kmajor(b_addr + k * UMMA_K * 2), idesc,
+                              (uint32_t)((kb > kb0) | (k != 0)));
+                umma_commit(&empty[stage]);
+                if (kb == kb1 - 1) umma_commit(tfull);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4 && kb1 > kb0) {
+        // partial[split][r][n]: lane = output feature n, TMEM column = token row r -> coalesced over n
+        const int q = warp & 3;
+        const int n = m_blk * BM + q * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float* dst = partial + (size_t)split * R * N + n;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (n < N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < R) dst[(size_t)(c0 + j) * N] = __uint_as_float(v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -279,12 +402,61 @@ bool launch_cfg(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, 
     const int grid = tiles < num_sms() ? tiles : num_sms();
     const int vec = (sizeof(TC) == 2 ? 8 : 4);
     const int vec_ok = (ldc % vec == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    gemm_bf16_sm100_kernel<BN, TC><<<grid, 256, cfg::SMEM_BYTES, s>>>(ta, tb, C, ldc, M, N, K, e, vec_ok);
+    launch_kernel(gemm_bf16_sm100_kernel<BN, TC>, dim3(grid), dim3(256), (size_t)cfg::SMEM_BYTES, s, true, ta, tb, C, ldc, M, N, K, e, vec_ok);
     count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { g_err = std::string("gemm launch: ") + cudaGetErrorString(err); return false; }
     return true;
 }
+
+
+template <int BN>
+bool launch_skinny_cfg(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int splits, int kb_per_split,
+                       cudaStream_t s) {
+    constexpr int STAGES = kSkinnyStages;
+    constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
+    CUtensorMap tw, tx;
+    if (!make_tmap_bf16_2d(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BM)) return false;
+    if (!make_tmap_bf16_2d(&tx, X, (uint64_t)K, (uint64_t)R, (uint64_t)ldx, BK, BN)) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_skinny_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+            g_err = "cudaFuncSetAttribute(skinny smem) failed";
+            return false;
+        }
+        configured = true;
+    }
+    dim3 grid((N + BM - 1) / BM, splits);
+    launch_kernel(gemm_skinny_sm100_kernel<BN>, grid, dim3(256), (size_t)SMEM, s, true, tw, tx, partial, R, N, K, kb_per_split);
+    count_launch();
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { g_err = std::string("skinny gemm launch: ") + cudaGetErrorString(err); return false; }
+    return true;
+}
+
+}  // namespace
+
+int skinny_gemm_splits(int N, int K) {
+    const int m_tiles = (N + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+    int splits = num_sms() / m_tiles;                       // one wave: never more CTAs than SMs ...
+    splits = std::max(1, std::min(splits, num_k / 2));      // ... and at least two k-blocks per CTA
+    const int kb_per = (num_k + splits - 1) / splits;
+    return (num_k + kb_per - 1) / kb_per;                   // no empty splits
+}
+
+bool launch_gemm_skinny_bf16_sm100(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int* splits_out,
+                                   cudaStream_t s) {
+    if (R <= 0 || R > 128 || N <= 0 || K <= 0) { g_err = "skinny gemm: bad shape"; return false; }
+    const int num_k = (K + BK - 1) / BK;
+    const int splits = skinny_gemm_splits(N, K);
+    const int kb_per = (num_k + splits - 1) / splits;
+    *splits_out = splits;
+    if (R <= 32) return launch_skinny_cfg<32>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+    if (R <= 64) return launch_skinny_cfg<64>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+    return launch_skinny_cfg<128>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+}
+
+namespace {
 
 template <typename TC>
 bool dispatch(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {

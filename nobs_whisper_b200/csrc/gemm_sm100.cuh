@@ -9,6 +9,12 @@ namespace nobs {
 // encoded or the launch fails.
 bool launch_gemm_bf16_sm100(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, bool c_is_f32, int M, int N, int K,
                             const Epilogue& e, cudaStream_t s);
+// Decoder-step GEMM (R <= 128 token rows), swap-AB + split-K on tcgen05: writes fp32 partial sums
+// partial[split][R][N] (the workspace must hold skinny_gemm_splits(N, K) * R * N floats); the caller
+// finishes with launch_skinny_reduce (kernels.cuh).
+int skinny_gemm_splits(int N, int K);
+bool launch_gemm_skinny_bf16_sm100(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int* splits_out,
+                                   cudaStream_t s);
 // Non-causal encoder self-attention over 1500 keys per window, head size 64.
 bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s);
 const char* sm100_last_error();

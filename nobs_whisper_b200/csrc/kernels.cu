@@ -8,9 +8,11 @@
 #include <atomic>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace nobs {
 
+bool g_use_pdl = [] { const char* e = getenv("NOBS_WHISPER_PDL"); return !(e && *e == '0'); }();
 static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -263,6 +265,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ idx,
                                                         const float* __restrict__ g, const float* __restrict__ b, TO* __restrict__ y,
                                                         int ldy, int rows, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -281,14 +285,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename TO>
 void launch_layernorm(const float* x, int ldx, const float* g, const float* b, TO* y, int ldy, int rows, int d, cudaStream_t s) {
     if (rows <= 0) return;
-    layernorm_kernel<TO><<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, nullptr, g, b, y, ldy, rows, d);
+    launch_kernel(layernorm_kernel<TO>, dim3((rows + 7) / 8), dim3(256), 0, s, true, x, ldx, (const int*)nullptr, g, b, y, ldy, rows, d);
     NOBS_COUNT_LAUNCH();
 }
 template <typename TO>
 void launch_layernorm_gather(const float* x, int ldx, const int* idx, const float* g, const float* b, TO* y, int ldy, int rows, int d,
                              cudaStream_t s) {
     if (rows <= 0) return;
-    layernorm_kernel<TO><<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, idx, g, b, y, ldy, rows, d);
+    launch_kernel(layernorm_kernel<TO>, dim3((rows + 7) / 8), dim3(256), 0, s, true, x, ldx, idx, g, b, y, ldy, rows, d);
     NOBS_COUNT_LAUNCH();
 }
 template void launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, int, int, cudaStream_t);
@@ -506,15 +510,25 @@ template void launch_scatter_kv<bf16>(const RowDesc*, int, const bf16*, bf16*, b
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
     static constexpr int N = 4;
-    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(p));
-        v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+    typedef float4 Raw;
+    static __device__ __forceinline__ Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ Raw load(const float* p) {  // streaming: read once, do not keep in L1
+        Raw r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
     }
+    static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[4]) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
 };
 template <> struct Vec16<bf16> {
     static constexpr int N = 8;
-    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ Raw load(const bf16* p) {
+        Raw r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[8]) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -525,6 +539,7 @@ template <> struct Vec16<bf16> {
 };
 
 constexpr int DA_THREADS = 256;
+constexpr int DA_UNROLL = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
@@ -537,6 +552,8 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
     __shared__ float sc[kWinRows];
     __shared__ float red[32];
     __shared__ float part[KPI][64 + 1];
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const RowDesc rd = rows[r];
     const int nk = cross ? n_keys : rd.pos + 1;
@@ -550,23 +567,23 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
 #pragma unroll
     for (int i = 0; i < VN; ++i) qv[i] = qs[sub * VN + i];
 
-    // scores: 4 keys per thread in flight
+    // scores: DA_UNROLL key rows per thread in flight (16-byte loads issued back to back, converted at use)
     float lmax = -INFINITY;
-    for (int j0 = 0; j0 < nk; j0 += 4 * KPI) {
-        float kv[4][VN];
+    for (int j0 = 0; j0 < nk; j0 += DA_UNROLL * KPI) {
+        typename Vec16<T>::Raw raw[DA_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DA_UNROLL; ++u) {
             const int j = j0 + u * KPI + ks;
-            if (j < nk) Vec16<T>::load(K + (size_t)j * 64 + sub * VN, kv[u]);
+            raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DA_UNROLL; ++u) {
             const int j = j0 + u * KPI + ks;
+            float kvv[VN];
+            Vec16<T>::unpack(raw[u], kvv);
             float acc = 0.0f;
-            if (j < nk) {
 #pragma unroll
-                for (int i = 0; i < VN; ++i) acc = fmaf(qv[i], kv[u][i], acc);
-            }
+            for (int i = 0; i < VN; ++i) acc = fmaf(qv[i], kvv[i], acc);
 #pragma unroll
             for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (j < nk) {
@@ -590,21 +607,21 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
     float acc[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
-    for (int j0 = 0; j0 < nk; j0 += 4 * KPI) {
-        float vv[4][VN];
+    for (int j0 = 0; j0 < nk; j0 += DA_UNROLL * KPI) {
+        typename Vec16<T>::Raw raw[DA_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DA_UNROLL; ++u) {
             const int j = j0 + u * KPI + ks;
-            if (j < nk) Vec16<T>::load(V + (size_t)j * 64 + sub * VN, vv[u]);
+            raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DA_UNROLL; ++u) {
             const int j = j0 + u * KPI + ks;
-            if (j < nk) {
-                const float p = sc[j];
+            const float p = j < nk ? sc[j] : 0.0f;
+            float vvv[VN];
+            Vec16<T>::unpack(raw[u], vvv);
 #pragma unroll
-                for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, vv[u][i], acc[i]);
-            }
+            for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, vvv[i], acc[i]);
         }
     }
 #pragma unroll
@@ -617,12 +634,113 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
         out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o * inv);
     }
 }
+// Causal self-attention over the (short) self-KV panel: one warp per (row, head), no block barriers.
+// At most 448 keys: the block-per-head kernel above is latency-bound there (4 resident blocks per SM
+// each paying several barrier round trips); a warp streams its <= 56 KB panel with shuffles only.
+template <typename T>
+__global__ void __launch_bounds__(128) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+                                                                 const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
+                                                                 int n_head, size_t slot_stride, size_t head_stride) {
+    constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, UNR = 8;
+    __shared__ float sc[4][448];
+    __shared__ float qs[4][64];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x, h = blockIdx.y * 4 + warp;
+    if (h >= n_head) return;
+    const RowDesc rd = rows[r];
+    const int nk = min(rd.pos + 1, 448);
+    const size_t base = (size_t)rd.kv_slot * slot_stride + (size_t)h * head_stride;
+    const T* K = kc + base;
+    const T* V = vc + base;
+    qs[warp][lane] = to_f32(q[(size_t)r * ldq + h * 64 + lane]);
+    qs[warp][lane + 32] = to_f32(q[(size_t)r * ldq + h * 64 + lane + 32]);
+    __syncwarp();
+    const int sub = lane % LPK, ks = lane / LPK;
+    float qv[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) qv[i] = qs[warp][sub * VN + i];
+    float* s_w = sc[warp];
+    float lmax = -INFINITY;
+    for (int j0 = 0; j0 < nk; j0 += UNR * KPW) {
+        typename Vec16<T>::Raw raw[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u * KPW + ks;
+            raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u * KPW + ks;
+            float kvv[VN];
+            Vec16<T>::unpack(raw[u], kvv);
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc = fmaf(qv[i], kvv[i], acc);
+#pragma unroll
+            for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (j < nk) {
+                acc *= 0.125f;
+                if (sub == 0) s_w[j] = acc;
+                lmax = fmaxf(lmax, acc);
+            }
+        }
+    }
+    const float mx = warp_max(lmax);
+    __syncwarp();
+    float lsum = 0.0f;
+    for (int j = lane; j < nk; j += 32) {
+        const float p = expf(s_w[j] - mx);
+        s_w[j] = p;
+        lsum += p;
+    }
+    const float inv = 1.0f / warp_sum(lsum);
+    __syncwarp();
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+    for (int j0 = 0; j0 < nk; j0 += UNR * KPW) {
+        typename Vec16<T>::Raw raw[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u * KPW + ks;
+            raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u * KPW + ks;
+            const float p = j < nk ? s_w[j] : 0.0f;
+            float vvv[VN];
+            Vec16<T>::unpack(raw[u], vvv);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, vvv[i], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+#pragma unroll
+        for (int o = 16; o >= LPK; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (ks == 0) {
+        T* dst = out + (size_t)r * ldo + h * 64 + sub * VN;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) dst[i] = from_f32<T>(acc[i] * inv);
+    }
+}
+
 template <typename T>
 void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
                           int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s) {
     if (n_rows <= 0) return;
+    if (!cross) {
+        dim3 grid(n_rows, (n_head + 3) / 4);
+        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, s, true, rows, q, ldq, kbase, vbase, out, ldo, n_head, slot_stride, head_stride);
+        NOBS_COUNT_LAUNCH();
+        return;
+    }
     dim3 grid(n_rows, n_head);
-    dec_attention_kernel<T><<<grid, DA_THREADS, 0, s>>>(rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, head_stride, n_keys);
+    launch_kernel(dec_attention_kernel<T>, grid, dim3(DA_THREADS), 0, s, true, rows, q, ldq, kbase, vbase, out, ldo, cross, slot_stride, head_stride, n_keys);
     NOBS_COUNT_LAUNCH();
 }
 template void launch_dec_attention<float>(const RowDesc*, int, const float*, int, const float*, const float*, float*, int, int, int, size_t, size_t,
@@ -648,6 +766,101 @@ void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_strid
 }
 template void launch_kv_copy<float>(const KvCopy*, int, float*, size_t, int, size_t, cudaStream_t);
 template void launch_kv_copy<bf16>(const KvCopy*, int, bf16*, size_t, int, size_t, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// skinny-GEMM epilogue: one token row per block
+// ------------------------------------------------------------------------------------------
+constexpr int SR_THREADS = 256;
+constexpr int SR_MAXV = 20;  // N <= 5120
+
+template <typename T>
+__global__ void __launch_bounds__(SR_THREADS) skinny_reduce_kernel(SkinnyEpilogue e) {
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const size_t plane = (size_t)e.R * e.N;
+    const float* p = e.partial + (size_t)r * e.N;
+    float vals[SR_MAXV];
+    RowDesc rd{};
+    if (e.rows) rd = e.rows[r];
+    // split-K sum, splits outermost: every iteration issues all of this thread's (independent) loads
+    // back to back instead of one dependent L2 round trip per addend
+#pragma unroll
+    for (int i = 0; i < SR_MAXV; ++i) vals[i] = 0.0f;
+    const int nv = (e.N + SR_THREADS - 1) / SR_THREADS;
+    int s0 = 0;
+    for (; s0 + 4 <= e.splits; s0 += 4) {   // four planes per trip: 4 * nv independent loads in flight
+        const float* ps = p + (size_t)s0 * plane;
+        float t[4][SR_MAXV];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < SR_MAXV; ++i) {
+                const int n = tid + i * SR_THREADS;
+                t[u][i] = (i < nv && n < e.N) ? __ldcg(ps + (size_t)u * plane + n) : 0.0f;
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < SR_MAXV; ++i) vals[i] += t[u][i];   // fixed order s0, s0+1, ...: deterministic
+    }
+    for (; s0 < e.splits; ++s0) {
+        const float* ps = p + (size_t)s0 * plane;
+#pragma unroll
+        for (int i = 0; i < SR_MAXV; ++i) {
+            const int n = tid + i * SR_THREADS;
+            if (i < nv && n < e.N) vals[i] += __ldcg(ps + n);
+        }
+    }
+    float lsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < SR_MAXV; ++i) {
+        const int n = tid + i * SR_THREADS;
+        if (i < nv && n < e.N) {
+            float v = vals[i];
+            if (e.bias) v += __ldg(e.bias + n);
+            if (e.act == 1) v = gelu_tanh_fast(v);
+            if (e.x) {
+                v += e.x[(size_t)r * e.N + n];
+                e.x[(size_t)r * e.N + n] = v;
+            }
+            if (e.out) static_cast<T*>(e.out)[(size_t)r * e.out_ld + n] = from_f32<T>(v);
+            if (e.rows && n >= e.d) {
+                const int c = n - e.d, which = c >= e.d, i2 = which ? c - e.d : c;
+                T* panel = static_cast<T*>(which ? e.vpanel : e.kpanel);
+                panel[(size_t)rd.kv_slot * e.slot_stride + ((size_t)(i2 >> 6) * e.n_pos_cap + rd.pos) * 64 + (i2 & 63)] = from_f32<T>(v);
+            }
+            lsum += v;
+            vals[i] = v;
+        }
+    }
+    if (e.ln_g) {
+        const float mean = block_reduce(lsum, 0.0f, OpAddF(), red) / e.N;
+        float lvar = 0.0f;
+#pragma unroll
+        for (int i = 0; i < SR_MAXV; ++i) {
+            const int n = tid + i * SR_THREADS;
+            if (n < e.N) { const float t = vals[i] - mean; lvar += t * t; }
+        }
+        const float var = block_reduce(lvar, 0.0f, OpAddF(), red) / e.N;
+        const float inv = rsqrtf(var + 1e-5f);
+        T* y = static_cast<T*>(e.y) + (size_t)r * e.N;
+#pragma unroll
+        for (int i = 0; i < SR_MAXV; ++i) {
+            const int n = tid + i * SR_THREADS;
+            if (n < e.N) y[n] = from_f32<T>((vals[i] - mean) * inv * __ldg(e.ln_g + n) + __ldg(e.ln_b + n));
+        }
+    }
+}
+template <typename T>
+void launch_skinny_reduce(const SkinnyEpilogue& e, cudaStream_t s) {
+    if (e.R <= 0) return;
+    launch_kernel(skinny_reduce_kernel<T>, dim3(e.R), dim3(SR_THREADS), 0, s, true, e);
+    NOBS_COUNT_LAUNCH();
+}
+template void launch_skinny_reduce<bf16>(const SkinnyEpilogue&, cudaStream_t);
+template void launch_skinny_reduce<float>(const SkinnyEpilogue&, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // K6: logit filter + log-softmax + timestamp rule + argmax / sample / top-k, one block per row.
@@ -680,6 +893,8 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
     __shared__ int s_pick;
     __shared__ int s_chosen[kMaxTopK];
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x, tid = threadIdx.x;
     const SampleParams p = params[row];
     const float* lg = logits + (size_t)row * ld;
@@ -842,7 +1057,7 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
 void launch_process_logits(const float* logits, int ld, const SampleParams* params, SampleResult* results, int n_rows, const VocabIds& v,
                            float* logprobs_out, float* probs_out, cudaStream_t s) {
     if (n_rows <= 0) return;
-    process_logits_kernel<<<n_rows, PL_THREADS, 0, s>>>(logits, ld, params, results, v, logprobs_out, probs_out);
+    launch_kernel(process_logits_kernel, dim3(n_rows), dim3(PL_THREADS), 0, s, true, logits, ld, params, results, v, logprobs_out, probs_out);
     NOBS_COUNT_LAUNCH();
 }
 

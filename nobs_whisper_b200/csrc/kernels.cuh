@@ -107,6 +107,30 @@ struct KvCopy {
 template <typename T>
 void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_panels, size_t panel_stride, cudaStream_t s);
 
+// ---------------------------------------------------------------- skinny-GEMM epilogue (decoder steps)
+// Sums the split-K partials of gemm_skinny (fixed order: deterministic) for one token row per block and
+// applies everything that used to be separate launches: bias, GELU, residual add into the fp32 stream,
+// the next LayerNorm, and the scatter of fresh K/V rows into the head-major self-KV panels.
+struct SkinnyEpilogue {
+    const float* partial = nullptr;  // [splits][R][N]
+    int splits = 0, R = 0, N = 0;
+    const float* bias = nullptr;     // [N]
+    int act = 0;                     // 1: GELU
+    float* x = nullptr;              // residual stream [R][N] fp32: x += v (v becomes the updated x)
+    void* out = nullptr;             // T [R][out_ld]: out = v
+    int out_ld = 0;
+    const float* ln_g = nullptr;     // if set: y = LayerNorm(v) * g + b as T [R][N]
+    const float* ln_b = nullptr;
+    void* y = nullptr;
+    const RowDesc* rows = nullptr;   // if set (QKV): columns [d,2d) / [2d,3d) also go to the K / V panels
+    void* kpanel = nullptr;
+    void* vpanel = nullptr;
+    size_t slot_stride = 0;
+    int n_pos_cap = 0, d = 0;
+};
+template <typename T>
+void launch_skinny_reduce(const SkinnyEpilogue& e, cudaStream_t s);
+
 // ---------------------------------------------------------------- K6 logits -> token
 struct VocabIds {
     int n_vocab, eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank, n_lang;
@@ -142,6 +166,23 @@ void launch_convert(const TI* in, TO* out, size_t n, cudaStream_t s);
 // strided 2D copy with conversion: out[r][c] = in[r*ld_in + c]
 template <typename TI, typename TO>
 void launch_convert_2d(const TI* in, size_t ld_in, TO* out, size_t ld_out, int rows, int cols, cudaStream_t s);
+
+// Launch with (or without) the programmatic-dependent-launch attribute.
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 long kernel_launch_count();  // process-wide count of kernels launched through these launchers
 void count_launch();
