@@ -1,0 +1,184 @@
+//! The whisper-rs surface used by `src-tauri/src/whisper.rs` (lines 3, 39-45, 83-141), re-implemented
+//! over the B200 library.  Names, argument meaning and error behaviour follow whisper-rs 0.15 so that
+//! the reference compiles against this crate unchanged (Cargo.toml: replace the `whisper-rs`
+//! dependency by `whisper-rs = { package = "nobs-whisper-b200", path = ".../rust/nobs-whisper-b200" }`).
+use nobs_whisper_b200_sys as sys;
+use std::borrow::Cow;
+use std::ffi::{CStr, CString};
+use std::fmt;
+use std::os::raw::c_int;
+use std::sync::Arc;
+
+#[derive(Debug)]
+pub enum WhisperError {
+    InitError,
+    NoSamples,
+    NullByteInString,
+    UnableToCalculateSpectrogram,
+    FailedToEncode,
+    FailedToDecode,
+    GenericError(c_int),
+}
+impl fmt::Display for WhisperError {
+    fn fmt(&self, f: &mut fmt::Formatter<'_>) -> fmt::Result {
+        let detail = unsafe { CStr::from_ptr(sys::whisper_b200_last_error()) }.to_string_lossy();
+        write!(f, "{:?}: {}", self, detail)
+    }
+}
+impl std::error::Error for WhisperError {}
+
+#[derive(Clone, Copy)]
+pub struct WhisperContextParameters {
+    inner: sys::whisper_context_params,
+}
+impl Default for WhisperContextParameters {
+    fn default() -> Self {
+        Self { inner: unsafe { sys::whisper_context_default_params() } }
+    }
+}
+impl WhisperContextParameters {
+    pub fn use_gpu(&mut self, v: bool) -> &mut Self {
+        self.inner.use_gpu = v; // accepted and ignored: the library has only the GPU path
+        self
+    }
+    pub fn gpu_device(&mut self, d: c_int) -> &mut Self {
+        self.inner.gpu_device = d;
+        self
+    }
+}
+
+struct CtxPtr(*mut sys::whisper_context);
+unsafe impl Send for CtxPtr {}
+unsafe impl Sync for CtxPtr {} // the C side serialises GPU work per context with a mutex
+impl Drop for CtxPtr {
+    fn drop(&mut self) {
+        unsafe { sys::whisper_free(self.0) }
+    }
+}
+
+#[derive(Clone)]
+pub struct WhisperContext {
+    ctx: Arc<CtxPtr>,
+}
+impl WhisperContext {
+    pub fn new_with_params(path: &str, params: WhisperContextParameters) -> Result<Self, WhisperError> {
+        let c = CString::new(path).map_err(|_| WhisperError::NullByteInString)?;
+        let p = unsafe { sys::whisper_init_from_file_with_params_no_state(c.as_ptr(), params.inner) };
+        if p.is_null() { Err(WhisperError::InitError) } else { Ok(Self { ctx: Arc::new(CtxPtr(p)) }) }
+    }
+    pub fn create_state(&self) -> Result<WhisperState, WhisperError> {
+        let s = unsafe { sys::whisper_init_state(self.ctx.0) };
+        if s.is_null() { Err(WhisperError::InitError) } else { Ok(WhisperState { ctx: self.ctx.clone(), ptr: s }) }
+    }
+}
+
+pub enum SamplingStrategy {
+    Greedy { best_of: c_int },
+    BeamSearch { beam_size: c_int, patience: f32 },
+}
+
+pub struct FullParams<'a, 'b> {
+    fp: sys::whisper_full_params,
+    language: Option<CString>,
+    initial_prompt: Option<CString>,
+    _phantom: std::marker::PhantomData<(&'a (), &'b ())>,
+}
+impl<'a, 'b> FullParams<'a, 'b> {
+    pub fn new(strategy: SamplingStrategy) -> Self {
+        let mut fp = unsafe {
+            sys::whisper_full_default_params(match strategy {
+                SamplingStrategy::Greedy { .. } => sys::WHISPER_SAMPLING_GREEDY,
+                SamplingStrategy::BeamSearch { .. } => sys::WHISPER_SAMPLING_BEAM_SEARCH,
+            })
+        };
+        match strategy {
+            SamplingStrategy::Greedy { best_of } => fp.greedy.best_of = best_of,
+            SamplingStrategy::BeamSearch { beam_size, patience } => {
+                fp.beam_search.beam_size = beam_size;
+                fp.beam_search.patience = patience;
+            }
+        }
+        Self { fp, language: None, initial_prompt: None, _phantom: std::marker::PhantomData }
+    }
+    pub fn set_language(&mut self, lang: Option<&str>) {
+        self.language = lang.and_then(|l| CString::new(l).ok());
+        self.fp.language = self.language.as_ref().map_or(std::ptr::null(), |c| c.as_ptr());
+    }
+    pub fn set_initial_prompt(&mut self, prompt: &str) {
+        self.initial_prompt = CString::new(prompt).ok();
+        self.fp.initial_prompt = self.initial_prompt.as_ref().map_or(std::ptr::null(), |c| c.as_ptr());
+    }
+    pub fn set_print_special(&mut self, v: bool) { self.fp.print_special = v }
+    pub fn set_print_progress(&mut self, v: bool) { self.fp.print_progress = v }
+    pub fn set_print_realtime(&mut self, v: bool) { self.fp.print_realtime = v }
+    pub fn set_print_timestamps(&mut self, v: bool) { self.fp.print_timestamps = v }
+    pub fn set_translate(&mut self, v: bool) { self.fp.translate = v }
+    pub fn set_no_context(&mut self, v: bool) { self.fp.no_context = v }
+    pub fn set_single_segment(&mut self, v: bool) { self.fp.single_segment = v }
+    pub fn set_suppress_blank(&mut self, v: bool) { self.fp.suppress_blank = v }
+    pub fn set_no_speech_thold(&mut self, v: f32) { self.fp.no_speech_thold = v }
+    pub fn set_entropy_thold(&mut self, v: f32) { self.fp.entropy_thold = v }
+    pub fn set_logprob_thold(&mut self, v: f32) { self.fp.logprob_thold = v }
+}
+
+pub struct WhisperState {
+    ctx: Arc<CtxPtr>,
+    ptr: *mut sys::whisper_state,
+}
+unsafe impl Send for WhisperState {}
+impl Drop for WhisperState {
+    fn drop(&mut self) {
+        unsafe { sys::whisper_free_state(self.ptr) }
+    }
+}
+impl WhisperState {
+    pub fn full(&mut self, params: FullParams, data: &[f32]) -> Result<c_int, WhisperError> {
+        if data.is_empty() {
+            return Err(WhisperError::NoSamples);
+        }
+        let ret = unsafe { sys::whisper_full_with_state(self.ctx.0, self.ptr, params.fp, data.as_ptr(), data.len() as c_int) };
+        match ret {
+            0 => Ok(ret),
+            -1 => Err(WhisperError::UnableToCalculateSpectrogram),
+            7 => Err(WhisperError::FailedToEncode),
+            8 => Err(WhisperError::FailedToDecode),
+            e => Err(WhisperError::GenericError(e)),
+        }
+    }
+    pub fn full_n_segments(&self) -> c_int {
+        unsafe { sys::whisper_full_n_segments_from_state(self.ptr) }
+    }
+    pub fn get_segment(&self, i: c_int) -> Option<WhisperSegment<'_>> {
+        if i >= 0 && i < self.full_n_segments() { Some(WhisperSegment { state: self, idx: i }) } else { None }
+    }
+}
+
+pub struct WhisperSegment<'a> {
+    state: &'a WhisperState,
+    idx: c_int,
+}
+impl<'a> WhisperSegment<'a> {
+    pub fn to_str_lossy(&self) -> Result<Cow<'a, str>, WhisperError> {
+        let p = unsafe { sys::whisper_full_get_segment_text_from_state(self.state.ptr, self.idx) };
+        if p.is_null() {
+            return Err(WhisperError::GenericError(-1));
+        }
+        Ok(unsafe { CStr::from_ptr(p) }.to_string_lossy())
+    }
+    pub fn start_timestamp(&self) -> i64 {
+        unsafe { sys::whisper_full_get_segment_t0_from_state(self.state.ptr, self.idx) }
+    }
+    pub fn end_timestamp(&self) -> i64 {
+        unsafe { sys::whisper_full_get_segment_t1_from_state(self.state.ptr, self.idx) }
+    }
+}
+
+/// B200 addition: `full` over independent audios in lock step.
+pub fn full_batch(ctx: &WhisperContext, states: &mut [WhisperState], params: FullParams, audios: &[&[f32]]) -> Result<Vec<c_int>, WhisperError> {
+    let st: Vec<*mut sys::whisper_state> = states.iter().map(|s| s.ptr).collect();
+    let ptrs: Vec<*const f32> = audios.iter().map(|a| a.as_ptr()).collect();
+    let ns: Vec<c_int> = audios.iter().map(|a| a.len() as c_int).collect();
+    let mut rc = vec![0 as c_int; st.len()];
+    let r = unsafe { sys::whisper_b200_full_batch(ctx.ctx.0, st.as_ptr(), st.len() as c_int, params.fp, ptrs.as_ptr(), ns.as_ptr(), rc.as_mut_ptr()) };
+    if r != 0 { Err(WhisperError::GenericError(r)) } else { Ok(rc) }
+}
