@@ -17,6 +17,10 @@ bool launch_gemm_skinny_bf16_sm100(const bf16* X, int ldx, const bf16* W, int ld
                                    cudaStream_t s);
 // Non-causal encoder self-attention over 1500 keys per window, head size 64.
 bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int n_head, int d, cudaStream_t s);
+// Decoder cross-attention over the head-major cross-KV panels for single-token rows (bf16): persistent,
+// one small CTA per SM fed by a cp.async.bulk ring (cross_attention_sm100.cu).  max_ctas > 0 caps the grid.
+bool launch_dec_cross_attention_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* kbase, const bf16* vbase, bf16* out, int ldo,
+                                      int n_head, size_t slot_stride, size_t head_stride, int n_keys, int max_ctas, cudaStream_t s);
 const char* sm100_last_error();
 
 }  // namespace nobs
