@@ -349,8 +349,15 @@ int whisper_b200_debug_gemm_bf16(int M, int N, int K, int lda, const float* A, s
  * head size 64).  qkv: [n_win*1536][3*64*n_head] fp32 (q|k|v), out: [n_win*1536][64*n_head] fp32. */
 int whisper_b200_debug_enc_attention(int n_win, int n_head, const float* qkv, float* out, int use_simt);
 
+/* Kernel-level test hook: decoder cross-attention of R single-token rows over head-major K/V panels
+ * (k, v: [n_slots][n_head][1536][64] fp32, rounded to bf16 on the device; row r uses slot r % n_slots and
+ * keys 0..n_keys-1).  streaming: 2 = tcgen05 streaming kernel, 1 = SIMT cp.async.bulk streaming kernel,
+ * 0 = block-per-head SIMT kernel. */
+int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n_keys, const float* q, const float* k, const float* v, float* out,
+                                           int streaming);
+
 /* Micro-benchmark hook: average device microseconds per launch of the decoder-step kernels for R token
- * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..10]). */
+ * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..12]; out_us holds 16 floats). */
 int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us);
 
 /* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */

@@ -191,6 +191,7 @@ SIGNATURES = {
                                                C.c_int, fp]),
     "whisper_b200_set_profiling": (None, [vp, C.c_int]),
     "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
+    "whisper_b200_debug_dec_cross_attention": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, C.c_int]),
     "whisper_b200_debug_time_decode_kernels": (C.c_int, [C.c_int, C.c_int, C.c_int, fp]),
     "whisper_b200_event_record": (C.c_int, [vp, C.c_int]),
     "whisper_b200_event_elapsed_ms": (C.c_double, [vp, C.c_int, C.c_int]),

@@ -311,7 +311,7 @@ int whisper_lang_auto_detect_with_state(struct whisper_context* ctx, struct whis
     Engine& e = *ctx->engine;
     std::lock_guard<std::mutex> lock(e.mu);
     int best = -1;
-    if (!e.lang_probs(0, lang_probs, &best)) { set_last_error(e.last_error()); return -7; }
+    if (!e.lang_probs(0, 0, lang_probs, &best)) { set_last_error(e.last_error()); return -7; }
     return best;
 }
 

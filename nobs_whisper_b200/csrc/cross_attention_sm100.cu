@@ -14,6 +14,8 @@
 //       block softmax, P*V with the same mapping, deterministic cross-warp sum.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "device_utils.cuh"
 #include "gemm_sm100.cuh"
 #include "sm100_ptx.cuh"
@@ -22,14 +24,12 @@ namespace nobs {
 
 namespace {
 
-constexpr int CA_WARPS = 8;                       // consumer warps
-constexpr int CA_THREADS = (CA_WARPS + 1) * 32;   // + producer warp
 constexpr int CA_CHUNK_KEYS = 128;
 constexpr int CA_ROW_BYTES = 64 * 2;
 constexpr int CA_CHUNK_BYTES = CA_CHUNK_KEYS * CA_ROW_BYTES;  // 16 KB
-constexpr int CA_STAGES = 6;
 constexpr int CA_MAX_KEYS = kWinRows;
-constexpr int CA_SMEM = CA_STAGES * CA_CHUNK_BYTES + CA_MAX_KEYS * 4 + CA_WARPS * 64 * 4 + 32 * 4 + 2 * CA_STAGES * 8 + 128;
+constexpr int CA_MAX_WARPS = 16;
+constexpr int ca_smem_bytes(int stages, int warps) { return stages * CA_CHUNK_BYTES + CA_MAX_KEYS * 4 + warps * 64 * 4 + 2 * CA_MAX_WARPS * 4 + 2 * stages * 8 + 128; }
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t p;
@@ -41,7 +41,8 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CA_WARPS * 32) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ uint4 lds128(const void* p) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
@@ -55,7 +56,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
     v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
-__global__ void __launch_bounds__(CA_THREADS, 1)
+template <int CA_STAGES, int CA_WARPS>
+__global__ void __launch_bounds__((CA_WARPS + 1) * 32, 1)
 dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, int n_head, const bf16* __restrict__ q, int ldq,
                                  const bf16* __restrict__ kc, const bf16* __restrict__ vc, bf16* __restrict__ out, int ldo, size_t slot_stride,
                                  size_t head_stride, int n_keys) {
@@ -63,8 +65,9 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
     uint8_t* ring = ca_smem;
     float* sc = reinterpret_cast<float*>(ring + CA_STAGES * CA_CHUNK_BYTES);
     float* part = sc + CA_MAX_KEYS;         // [CA_WARPS][64]
-    float* red = part + CA_WARPS * 64;      // [2][16]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 32);
+    float* red = part + CA_WARPS * 64;      // [2][CA_MAX_WARPS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * CA_MAX_WARPS);
+    constexpr int ITERS = CA_CHUNK_KEYS / (CA_WARPS * 4);
     uint64_t* empty = full + CA_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,11 +122,11 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
         for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(&full[stage], phase);
             const uint8_t* cb = ring + stage * CA_CHUNK_BYTES;
-            uint4 raw[4];
+            uint4 raw[ITERS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) raw[i] = lds128(cb + ((i * CA_WARPS + warp) * 4 + ks) * CA_ROW_BYTES + sub * 16);
+            for (int i = 0; i < ITERS; ++i) raw[i] = lds128(cb + ((i * CA_WARPS + warp) * 4 + ks) * CA_ROW_BYTES + sub * 16);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < ITERS; ++i) {
                 const int j = c * CA_CHUNK_KEYS + (i * CA_WARPS + warp) * 4 + ks;
                 float kv[8];
                 unpack8(raw[i], kv);
@@ -144,7 +147,7 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
         }
         lmax = warp_max(lmax);
         if (lane == 0) red[warp] = lmax;
-        consumer_sync();
+        consumer_sync<CA_WARPS * 32>();
         float mx = red[0];
 #pragma unroll
         for (int w = 1; w < CA_WARPS; ++w) mx = fmaxf(mx, red[w]);
@@ -155,11 +158,11 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
             lsum += p;
         }
         lsum = warp_sum(lsum);
-        if (lane == 0) red[16 + warp] = lsum;
-        consumer_sync();
+        if (lane == 0) red[CA_MAX_WARPS + warp] = lsum;
+        consumer_sync<CA_WARPS * 32>();
         float total = 0.0f;
 #pragma unroll
-        for (int w = 0; w < CA_WARPS; ++w) total += red[16 + w];   // fixed order
+        for (int w = 0; w < CA_WARPS; ++w) total += red[CA_MAX_WARPS + w];   // fixed order
         const float inv = 1.0f / total;
         // ---- P * V
         float acc[8];
@@ -168,16 +171,16 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
         for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(&full[stage], phase);
             const uint8_t* cb = ring + stage * CA_CHUNK_BYTES;
-            uint4 raw[4];
-            float p[4];
+            uint4 raw[ITERS];
+            float p[ITERS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < ITERS; ++i) {
                 const int jl = (i * CA_WARPS + warp) * 4 + ks, j = c * CA_CHUNK_KEYS + jl;
                 raw[i] = lds128(cb + jl * CA_ROW_BYTES + sub * 16);
                 p[i] = j < n_keys ? sc[j] : 0.0f;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < ITERS; ++i) {
                 float vv[8];
                 unpack8(raw[i], vv);
                 if (p[i] != 0.0f) {   // rows past n_keys of the last chunk hold stale bytes
@@ -198,7 +201,7 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
 #pragma unroll
             for (int e = 0; e < 8; ++e) part[warp * 64 + sub * 8 + e] = acc[e];
         }
-        consumer_sync();
+        consumer_sync<CA_WARPS * 32>();
         if (tid < 64) {
             float o = 0.0f;
 #pragma unroll
@@ -210,32 +213,385 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant: the same stream, but the shared-memory panels are read by tcgen05.mma instead of
+// by 256 threads, so the kernel leaves the SM's issue slots to the co-resident projection kernels.
+//
+//   S^T[128 keys, 16]  = K_chunk[128 x 64] * qB[16 x 64]^T     (row 0 of qB = q, rows 1..15 are don't-care:
+//                                                                 column n of D depends on row n of B only)
+//   O  [128, 64 dims] += P_tile[128 x 16 keys] * V_chunk[16 keys x 64]   (row 0 of P_tile = p, rows 1..127
+//                                                                 are whatever follows in shared memory:
+//                                                                 lane m of D depends on row m of A only)
+//   K/V chunks arrive through a TMA tensor map with the 128-byte swizzle the UMMA descriptors expect; V is
+//   the MN-major B operand, read in place.  All 12 score chunks of an item sit in 192 TMEM columns; 128
+//   threads (thread = TMEM lane = key within chunk) do the softmax on 12 registers each and write p as bf16.
+//   warps 0-3 softmax/output, warp 4 TMA producer, warp 5 MMA issuer.  256 TMEM columns, ~126 KB smem.
+constexpr int TC_P_BYTES = 4096;         // p of all 1536 keys as one linear bf16 row (3 KB used)
+constexpr int TC_Q_BYTES = 2 * 2048;     // two q tiles (double buffered across items)
+constexpr int tc_smem_bytes(int stages) { return TC_P_BYTES + TC_Q_BYTES + stages * CA_CHUNK_BYTES + 384 + 1024; }
+// K-major operand WITHOUT swizzle whose 8x16-byte core matrices overlap at a 16-byte pitch (LBO = 16 B): row 0 of
+// the tile is then a plain linear array; rows 1.. are the bytes that follow (don't-care rows).
+__device__ __forceinline__ uint64_t make_smem_desc_linear_row0(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+constexpr uint32_t TC_IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TC_IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ float tmem_ld_1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "l"(policy)
+                 : "memory");
+}
+
+// SP: TMEM column pitch between the score blocks of consecutive chunks.  16 = disjoint blocks (256 columns
+// allocated); 4 = overlapping blocks written in increasing order, each MMA's don't-care columns are overwritten by
+// the following chunk's real column (128 columns allocated, two CTAs fit next to the projection GEMMs).
+template <int TC_STAGES, int SP>
+__global__ void __launch_bounds__(192, 1)
+dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const RowDesc* __restrict__ rows, int n_items, int n_head,
+                              const bf16* __restrict__ q, int ldq, bf16* __restrict__ out, int ldo, long long k_row0, long long v_row0,
+                              long long slot_rows, int n_keys, int* __restrict__ sched) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    uint8_t* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr uint32_t TC_TMEM_COLS = SP == 16 ? 256 : 128;
+    constexpr uint32_t O_COL = SP == 16 ? 192 : 64;
+    constexpr int QD = 4;                             // item queue depth (the scheduler runs two items ahead)
+    uint8_t* sP = smem;                               // [1536] bf16
+    uint8_t* sQ = sP + TC_P_BYTES;                    // [2][2 KB]
+    uint8_t* ring = sQ + TC_Q_BYTES;                  // [TC_STAGES][16 KB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + TC_STAGES * CA_CHUNK_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* q_full = empty + TC_STAGES;             // 2
+    uint64_t* s_full = q_full + 2;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* o_full = p_full + 1;
+    uint64_t* item_full = o_full + 1;                 // QD
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(item_full + QD);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);   // [8]
+    int* item_q = reinterpret_cast<int*>(red + 8);          // [QD]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmap_kv);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+        for (int i = 0; i < QD; ++i) mbar_init(&item_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + O_COL;
+    const int n_chunks = (n_keys + CA_CHUNK_KEYS - 1) / CA_CHUNK_KEYS;
+
+    // Items ((row, head) pairs) are handed out by a device-wide counter: CTAs that become resident late (another
+    // lane's kernels hold the SM) simply take what is left, nothing is statically owned.  The scheduler thread
+    // publishes item `it` in item_q[it % QD]; -1 ends the stream.
+    auto next_item = [&](int it) -> int {
+        mbar_wait(&item_full[it % QD], (uint32_t)((it / QD) & 1));
+        return item_q[it % QD];
+    };
+
+    if (warp == 4) {
+        // ===== TMA producer: runs ahead across items; nothing here depends on the predecessor kernel =====
+        if (lane == 0) {
+            const uint64_t policy = l2_evict_first_policy();
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0;; ++it) {
+                const int item = next_item(it);
+                if (item < 0) break;
+                const int r = item / n_head, h = item - r * n_head;
+                const long long base = (long long)rows[r].audio_slot * slot_rows + (long long)h * kWinRows;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const long long row0 = base + (pass ? v_row0 : k_row0);
+                    for (int c = 0; c < n_chunks; ++c) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], CA_CHUNK_BYTES);
+                        tma_load_2d_hint(ring + stage * CA_CHUNK_BYTES, &tmap_kv, &full[stage], 0, (int)(row0 + c * CA_CHUNK_KEYS), policy);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            pdl_launch_dependents();
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0;; ++it) {
+            if (next_item(it) < 0) break;
+            const uint32_t qb_addr = smem_u32(sQ + (it & 1) * 2048);
+            mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t k_addr = smem_u32(ring + stage * CA_CHUNK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_S + (uint32_t)(c * SP), make_smem_desc_kmajor(k_addr + k * 32), make_smem_desc_kmajor(qb_addr + k * 32), TC_IDESC_S,
+                                  (uint32_t)(k != 0));
+                    umma_commit(&empty[stage]);
+                    if (c == n_chunks - 1) umma_commit(s_full);
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+            mbar_wait(p_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t v_addr = smem_u32(ring + stage * CA_CHUNK_BYTES), p_addr = smem_u32(sP + c * CA_CHUNK_KEYS * 2);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)   // 16 keys per MMA
+                        umma_bf16(tmem_O, make_smem_desc_linear_row0(p_addr + k * 32), make_smem_desc_mnmajor(v_addr + k * 16 * 128),
+                                  TC_IDESC_O, (uint32_t)((c | k) != 0));
+                    umma_commit(&empty[stage]);
+                    if (c == n_chunks - 1) umma_commit(o_full);
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== softmax + output: thread = TMEM lane = key within a chunk; thread 0 is also the item scheduler =====
+        const int row = warp * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        auto fetch = [&](int it) {   // thread 0 only
+            int item = atomicAdd(&sched[0], 1);
+            if (item >= n_items) item = -1;
+            item_q[it % QD] = item;
+            mbar_arrive(&item_full[it % QD]);   // release: the queue entry is visible to whoever completes the wait
+        };
+        if (threadIdx.x == 0) { fetch(0); fetch(1); }   // the counter does not depend on the predecessor kernel
+        pdl_wait();   // q does
+        auto put_q = [&](int item, int buf) {   // 128 bytes of q -> row 0 of the q tile (row 0 of a swizzle atom is stored linearly)
+            if (warp == 0) {
+                if (lane < 8) {
+                    const int r = item / n_head, h = item - r * n_head;
+                    const uint4 v = *reinterpret_cast<const uint4*>(q + (size_t)r * ldq + h * 64 + lane * 8);
+                    *reinterpret_cast<uint4*>(sQ + buf * 2048 + lane * 16) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_full[buf]);
+            }
+        };
+        int item = next_item(0);
+        if (item >= 0) put_q(item, 0);
+        for (int it = 0; item >= 0; ++it) {
+            const int r = item / n_head, h = item - r * n_head;
+            mbar_wait(s_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            float sv[12];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) sv[c] = c < n_chunks ? tmem_ld_1(tmem_S + lane_addr + (uint32_t)(c * SP)) : 0.0f;
+            tmem_ld_wait();
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                sv[c] = (c * CA_CHUNK_KEYS + row < n_keys) ? sv[c] * 0.125f : -INFINITY;
+                lmax = fmaxf(lmax, sv[c]);
+            }
+            lmax = warp_max(lmax);
+            if (lane == 0) red[warp] = lmax;
+            consumer_sync<128>();
+            const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+            float lsum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const bf16 pb = __float2bfloat16_rn(expf(sv[c] - mx));   // exp(-inf) = 0 for masked keys
+                lsum += __bfloat162float(pb);                            // the sum of what the tensor core will see
+                if (c < n_chunks) reinterpret_cast<bf16*>(sP)[c * CA_CHUNK_KEYS + row] = pb;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(p_full);
+            lsum = warp_sum(lsum);
+            if (lane == 0) red[4 + warp] = lsum;
+            if (threadIdx.x == 0) fetch(it + 2);
+            const int next = next_item(it + 1);
+            if (next >= 0) put_q(next, (it + 1) & 1);
+            consumer_sync<128>();
+            if (warp == 0) {
+                const float inv = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
+                mbar_wait(o_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                uint32_t o0[32], o1[32];
+                tmem_ld_32x32(tmem_O, o0);
+                tmem_ld_32x32(tmem_O + 32, o1);
+                tmem_ld_wait();
+                if (lane == 0) {
+                    bf16* dst = out + (size_t)r * ldo + h * 64;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 u;
+                        __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv);
+                        __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv);
+                        __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv);
+                        __nv_bfloat162 d2 = __floats2bfloat162_rn(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv);
+                        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+                        u.z = *reinterpret_cast<uint32_t*>(&c2); u.w = *reinterpret_cast<uint32_t*>(&d2);
+                        *reinterpret_cast<uint4*>(dst + i) = u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 u;
+                        __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv);
+                        __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv);
+                        __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv);
+                        __nv_bfloat162 d2 = __floats2bfloat162_rn(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv);
+                        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+                        u.z = *reinterpret_cast<uint32_t*>(&c2); u.w = *reinterpret_cast<uint32_t*>(&d2);
+                        *reinterpret_cast<uint4*>(dst + 32 + i) = u;
+                    }
+                }
+                tc_fence_before();
+            }
+            // the next item's first barrier (after its s_full wait) orders warp 0's O read before anyone
+            // arrives on the next p_full, i.e. before the next item's P*V can overwrite the accumulator
+            item = next;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+    // the last CTA to leave re-arms the counters for the next launch on this lane
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 }  // namespace
 
-int cross_attention_sm100_smem_bytes() { return CA_SMEM; }
+namespace {
+int env_or(const char* name, int dflt);
+template <int STAGES, int SP>
+bool launch_tc(const CUtensorMap& tm, const RowDesc* rows, int n_items, int n_head, const bf16* q, int ldq, bf16* out, int ldo, long long k_row0,
+               long long v_row0, long long slot_rows, int n_keys, int* sched, int grid, cudaStream_t s) {
+    constexpr int SMEM = tc_smem_bytes(STAGES);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(dec_cross_attention_tc_kernel<STAGES, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+            sm100_set_error("cudaFuncSetAttribute(cross attention tc smem) failed");
+            return false;
+        }
+        configured = true;
+    }
+    launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo, k_row0,
+                  v_row0, slot_rows, n_keys, sched);
+    return true;
+}
+}  // namespace
+
+bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
+                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s) {
+    if (n_rows <= 0) return true;
+    if (!sched || n_keys <= 0 || n_keys > CA_MAX_KEYS || (ldq % 8) != 0 || (slot_stride % 64) || (k_off % 64) || (v_off % 64) || pool_elems / 64 >= (1ull << 31)) {
+        sm100_set_error("cross attention (tc): unsupported shape");
+        return false;
+    }
+    static int sms = 0, stages = 0, sp = 0, per_sm = 1;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 8);
+        sp = env_or("NOBS_WHISPER_CROSS_SPACING", 16);
+        per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 1);
+    }
+    // one tensor map over the whole pool viewed as [rows][64] (re-encoded when the pool moves or grows)
+    thread_local const bf16* cached_pool = nullptr;
+    thread_local size_t cached_elems = 0;
+    thread_local CUtensorMap tm;
+    if (cached_pool != pool || cached_elems != pool_elems) {
+        if (!make_tmap_bf16_2d(&tm, pool, 64, pool_elems / 64, 64, 64, CA_CHUNK_KEYS)) return false;
+        cached_pool = pool;
+        cached_elems = pool_elems;
+    }
+    const int n_items = n_rows * n_head;
+    int grid = n_items < sms * per_sm ? n_items : sms * per_sm;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    bool ok = false;
+#define TC_CASE(S, P) if (stages == S && sp == P) ok = launch_tc<S, P>(tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, grid, s); else
+    TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
+    { sm100_set_error("cross attention (tc): unsupported NOBS_WHISPER_CROSS_STAGES / _SPACING"); return false; }
+#undef TC_CASE
+    if (!ok) return false;
+    count_launch();
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { sm100_set_error(std::string("cross attention (tc) launch: ") + cudaGetErrorString(err)); return false; }
+    return true;
+}
+
+namespace {
+int env_or(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+template <int STAGES, int WARPS>
+bool launch_ca(const RowDesc* rows, int n_items, int n_head, const bf16* q, int ldq, const bf16* kbase, const bf16* vbase, bf16* out, int ldo,
+               size_t slot_stride, size_t head_stride, int n_keys, int grid, cudaStream_t s) {
+    constexpr int SMEM = ca_smem_bytes(STAGES, WARPS);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(dec_cross_attention_sm100_kernel<STAGES, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+            sm100_set_error("cudaFuncSetAttribute(cross attention smem) failed");
+            return false;
+        }
+        configured = true;
+    }
+    launch_kernel(dec_cross_attention_sm100_kernel<STAGES, WARPS>, dim3(grid), dim3((WARPS + 1) * 32), (size_t)SMEM, s, true, rows, n_items, n_head, q, ldq,
+                  kbase, vbase, out, ldo, slot_stride, head_stride, n_keys);
+    return true;
+}
+}  // namespace
 
 bool launch_dec_cross_attention_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* kbase, const bf16* vbase, bf16* out, int ldo,
                                       int n_head, size_t slot_stride, size_t head_stride, int n_keys, int max_ctas, cudaStream_t s) {
     if (n_rows <= 0) return true;
     if (n_keys <= 0 || n_keys > CA_MAX_KEYS || (ldq % 8) != 0) { sm100_set_error("cross attention: unsupported shape"); return false; }
-    static bool configured = false;
-    static int sms = 0;
-    if (!configured) {
-        if (cudaFuncSetAttribute(dec_cross_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_SMEM) != cudaSuccess) {
-            sm100_set_error("cudaFuncSetAttribute(cross attention smem) failed");
-            return false;
-        }
+    static int sms = 0, stages = 0, warps = 0, per_sm = 1;
+    if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
-        configured = true;
+        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 6);
+        warps = env_or("NOBS_WHISPER_CROSS_WARPS", 8);
+        per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 1);
     }
     const int n_items = n_rows * n_head;
-    int grid = n_items < sms ? n_items : sms;
+    int grid = n_items < sms * per_sm ? n_items : sms * per_sm;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    launch_kernel(dec_cross_attention_sm100_kernel, dim3(grid), dim3(CA_THREADS), (size_t)CA_SMEM, s, true, rows, n_items, n_head, q, ldq, kbase, vbase, out,
-                  ldo, slot_stride, head_stride, n_keys);
+    bool ok = false;
+#define CA_CASE(S, W) if (stages == S && warps == W) ok = launch_ca<S, W>(rows, n_items, n_head, q, ldq, kbase, vbase, out, ldo, slot_stride, head_stride, n_keys, grid, s); else
+    CA_CASE(3, 8) CA_CASE(4, 8) CA_CASE(6, 8) CA_CASE(8, 8) CA_CASE(10, 8) CA_CASE(12, 8) CA_CASE(4, 16) CA_CASE(6, 16) CA_CASE(8, 16) CA_CASE(12, 16) CA_CASE(3, 4) CA_CASE(4, 4)
+    { sm100_set_error("cross attention: unsupported NOBS_WHISPER_CROSS_STAGES / _WARPS"); return false; }
+#undef CA_CASE
+    if (!ok) return false;
     count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { sm100_set_error(std::string("cross attention launch: ") + cudaGetErrorString(err)); return false; }

@@ -84,15 +84,65 @@ extern "C" int whisper_b200_debug_enc_attention(int n_win, int n_head, const flo
     return 0;
 }
 
+// Decoder cross-attention test hook: R single-token rows, row r attends over the n_keys keys of audio slot
+// r % n_slots.  q fp32 [R][64*n_head]; k, v fp32 [n_slots][n_head][1536][64] (head-major panels, rounded to
+// bf16 on the device); out fp32 [R][64*n_head].  streaming: 2 tcgen05 kernel, 1 SIMT cp.async.bulk kernel, 0 block-per-head SIMT kernel.
+extern "C" int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n_keys, const float* q, const float* k, const float* v,
+                                                      float* out, int streaming) {
+    if (R <= 0 || n_head <= 0 || n_slots <= 0 || n_keys <= 0 || n_keys > 1500 || !q || !k || !v || !out) return -1;
+    const int d = n_head * 64;
+    const size_t q_elems = (size_t)R * d, kv_elems = (size_t)n_slots * n_head * kWinRows * 64;
+    DevBuf dsched;
+    if (!dsched.alloc(256)) return -2;
+    cudaMemset(dsched.p, 0, 256);
+    DevBuf dqf, dq, dkvf, dkv, dout, doutf, drows;   // K panels of all slots, then V panels of all slots: one pool
+    if (!dqf.alloc(q_elems * 4) || !dq.alloc(q_elems * 2) || !dkvf.alloc(2 * kv_elems * 4) || !dkv.alloc(2 * kv_elems * 2) || !dout.alloc(q_elems * 2) ||
+        !doutf.alloc(q_elems * 4) || !drows.alloc(sizeof(RowDesc) * R))
+        return -2;
+    std::vector<RowDesc> hr(R);
+    for (int i = 0; i < R; ++i) hr[i] = RowDesc{0, 0, 0, i % n_slots};
+    cudaMemcpy(drows.p, hr.data(), sizeof(RowDesc) * R, cudaMemcpyHostToDevice);
+    cudaMemcpy(dqf.p, q, q_elems * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dkvf.p, k, kv_elems * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy((float*)dkvf.p + kv_elems, v, kv_elems * 4, cudaMemcpyHostToDevice);
+    cudaStream_t s = nullptr;
+    launch_convert<float, bf16>((const float*)dqf.p, (bf16*)dq.p, q_elems, s);
+    launch_convert<float, bf16>((const float*)dkvf.p, (bf16*)dkv.p, 2 * kv_elems, s);
+    cudaMemset(dout.p, 0xff, q_elems * 2);
+    const bf16* dk = (const bf16*)dkv.p;
+    const bf16* dv = dk + kv_elems;
+    const size_t slot_stride = (size_t)n_head * kWinRows * 64, head_stride = (size_t)kWinRows * 64;
+    bool ok = true;
+    if (streaming == 2) {
+        ok = launch_dec_cross_attention_tc_sm100((const RowDesc*)drows.p, R, (const bf16*)dq.p, d, dk, 2 * kv_elems, 0, kv_elems, (bf16*)dout.p, d, n_head, slot_stride,
+                                                 n_keys, (int*)dsched.p, 0, s);
+    } else if (streaming == 1) {
+        ok = launch_dec_cross_attention_sm100((const RowDesc*)drows.p, R, (const bf16*)dq.p, d, dk, dv, (bf16*)dout.p, d, n_head, slot_stride, head_stride, n_keys, 0, s);
+    } else {
+        launch_dec_attention<bf16>((const RowDesc*)drows.p, R, (const bf16*)dq.p, d, dk, dv, (bf16*)dout.p, d, n_head, 1, slot_stride, head_stride, n_keys, s);
+    }
+    if (!ok) {
+        set_last_error(std::string("debug_dec_cross_attention: ") + sm100_last_error());
+        return -3;
+    }
+    launch_convert<bf16, float>((const bf16*)dout.p, (float*)doutf.p, q_elems, s);
+    cudaMemcpyAsync(out, doutf.p, q_elems * 4, cudaMemcpyDeviceToHost, s);
+    const cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) { set_last_error(std::string("debug_dec_cross_attention: ") + cudaGetErrorString(err)); return -4; }
+    return 0;
+}
+
 // Micro-benchmark hook: average device time per launch (events around `iters` back-to-back launches) of
 // the decoder-step kernels at large-v3 dimensions for R token rows.  out_us[]: 0 skinny QKV (N=3d,K=d),
 // 1 skinny out (N=d,K=d), 2 skinny FC1 (N=4d,K=d), 3 skinny FC2 (N=d,K=4d), 4 reduce plain N=3d,
 // 5 reduce resid+LN N=d, 6 reduce gelu N=4d, 7 self-attention (100 keys), 8 cross-attention (1500 keys),
-// 9 generic GEMM N=d K=d (previous path), 10 layernorm.
+// 9 generic GEMM N=d K=d (previous path), 10 layernorm, 11 cross-attention (SIMT cp.async.bulk streaming kernel), 12 cross-attention (tcgen05 streaming kernel).
 extern "C" int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us) {
     if (R <= 0 || R > 128 || d % 64 || iters <= 0 || !out_us) return -1;
     const int H = d / 64, ntc = 448;
-    DevBuf x, y, big, att, W, partial, bias, g, kv, ckv, rows;
+    DevBuf x, y, big, att, W, partial, bias, g, kv, ckv, rows, sched;
+    if (!sched.alloc(256)) return -2;
+    cudaMemset(sched.p, 0, 256);
     const size_t wmax = (size_t)4 * d * d;
     if (!x.alloc((size_t)128 * d * 4) || !y.alloc((size_t)128 * 4 * d * 2) || !big.alloc((size_t)128 * 4 * d * 2) || !att.alloc((size_t)128 * d * 2) ||
         !W.alloc(wmax * 2) || !partial.alloc((size_t)16 << 20) || !bias.alloc((size_t)4 * d * 4) || !g.alloc((size_t)4 * d * 4) ||
@@ -140,6 +190,11 @@ extern "C" int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, f
                                                (bf16*)att.p, d, H, 0, (size_t)2 * ntc * d, (size_t)ntc * 64, 0, s); });
     timeit(8, [&] { launch_dec_attention<bf16>((const RowDesc*)rows.p, R, (const bf16*)big.p, d, (const bf16*)ckv.p, (const bf16*)ckv.p + (size_t)kWinRows * d,
                                                (bf16*)att.p, d, H, 1, (size_t)2 * kWinRows * d, (size_t)kWinRows * 64, 1500, s); });
+    timeit(11, [&] { launch_dec_cross_attention_sm100((const RowDesc*)rows.p, R, (const bf16*)big.p, d, (const bf16*)ckv.p, (const bf16*)ckv.p + (size_t)kWinRows * d,
+                                                      (bf16*)att.p, d, H, (size_t)2 * kWinRows * d, (size_t)kWinRows * 64, 1500, 0, s); });
+    unsigned tc_seq = 0;
+    timeit(12, [&] { launch_dec_cross_attention_tc_sm100((const RowDesc*)rows.p, R, (const bf16*)big.p, d, (const bf16*)ckv.p, (size_t)R * 2 * kWinRows * d, 0,
+                                                         (size_t)kWinRows * d, (bf16*)att.p, d, H, (size_t)2 * kWinRows * d, 1500, (int*)sched.p + ((tc_seq++ & 1u) << 1), 0, s); });
     timeit(9, [&] { Epilogue e; e.bias = (const float*)bias.p; launch_gemm_bf16_sm100(X, d, Wp, d, big.p, d, false, R, d, d, e, s); });
     timeit(10, [&] { launch_layernorm<bf16>((const float*)x.p, d, (const float*)g.p, (const float*)g.p, (bf16*)y.p, d, R, d, s); });
     // launch turnaround floor: the same tiny kernel chain (a) as stream launches, (b) as one CUDA graph

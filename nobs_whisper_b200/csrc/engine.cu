@@ -90,7 +90,15 @@ public:
             for (int i = 0; i < 8; ++i)
                 if (detail_n_[i]) fprintf(stderr, "[nobs profile] %-14s n=%8ld total=%10.2f ms avg=%8.2f us\n", names[i], detail_n_[i], detail_ms_[i], 1e3 * detail_ms_[i] / detail_n_[i]);
         }
-        for (auto& e : ev_pool_) cudaEventDestroy(e);
+        for (auto& e : main_marks_.pool) cudaEventDestroy(e);
+        for (auto& L : lanes_) {
+            if (L.stream) cudaStreamSynchronize(L.stream);
+            for (auto& e : L.tm.pool) cudaEventDestroy(e);
+            for (auto& e : L.ev) if (e) cudaEventDestroy(e);
+            if (L.pin) cudaFreeHost(L.pin);
+            if (L.scratch) cudaFree(L.scratch);
+            if (L.stream) cudaStreamDestroy(L.stream);
+        }
         for (auto& e : user_ev_) if (e) cudaEventDestroy(e);
         if (stream_) cudaStreamDestroy(stream_);
     }
@@ -215,34 +223,41 @@ public:
         return true;
     }
 
-    // ---- per-launch event timing (profiling mode)
-    void mark_begin() {
-        if (!profiling) return;
-        if (ev_used_ + 2 > ev_pool_.size()) {
-            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev_pool_.push_back(e); }
+    // ---- per-launch event timing (profiling mode); one context per stream
+    struct Marks {
+        cudaStream_t s = nullptr;
+        std::vector<cudaEvent_t> pool;
+        size_t used = 0;
+        std::vector<std::pair<int, int>> marks;
+    };
+    void mark_begin(Marks& m, bool on) {
+        if (!on) return;
+        if (m.used + 2 > m.pool.size()) {
+            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); m.pool.push_back(e); }
         }
-        cudaEventRecord(ev_pool_[ev_used_], stream_);
+        cudaEventRecord(m.pool[m.used], m.s);
     }
-    void mark_end(int cls) {
-        if (!profiling) return;
-        cudaEventRecord(ev_pool_[ev_used_ + 1], stream_);
-        marks_.push_back({cls, (int)ev_used_});
-        ev_used_ += 2;
+    void mark_end(Marks& m, bool on, int cls) {
+        if (!on) return;
+        cudaEventRecord(m.pool[m.used + 1], m.s);
+        m.marks.push_back({cls, (int)m.used});
+        m.used += 2;
     }
-    void dmark_begin() { if (detail_) { const bool p = profiling; profiling = true; mark_begin(); profiling = p; } }
-    void dmark_end(int cls) { if (detail_) { const bool p = profiling; profiling = true; mark_end(cls); profiling = p; } }
-    void collect_marks() {  // call after the stream has been synchronised
-        for (const auto& m : marks_) {
+    void collect_marks(Marks& m) {  // call after the stream has been synchronised
+        for (const auto& k : m.marks) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ev_pool_[m.second], ev_pool_[m.second + 1]);
-            if (m.first >= 10) { detail_ms_[m.first - 10] += ms; detail_n_[m.first - 10]++; }
-            else if (m.first == 0) { stats.ms_enc_gemm += ms; stats.n_enc_gemm++; }
-            else if (m.first == 1) { stats.ms_enc_attn += ms; stats.n_enc_attn++; }
+            cudaEventElapsedTime(&ms, m.pool[k.second], m.pool[k.second + 1]);
+            if (k.first >= 10) { detail_ms_[k.first - 10] += ms; detail_n_[k.first - 10]++; }
+            else if (k.first == 0) { stats.ms_enc_gemm += ms; stats.n_enc_gemm++; }
+            else if (k.first == 1) { stats.ms_enc_attn += ms; stats.n_enc_attn++; }
             else { stats.ms_dec_cross += ms; stats.n_dec_cross++; }
         }
-        marks_.clear();
-        ev_used_ = 0;
+        m.marks.clear();
+        m.used = 0;
     }
+    void mark_begin() { mark_begin(main_marks_, profiling); }
+    void mark_end(int cls) { mark_end(main_marks_, profiling, cls); }
+    void collect_marks() { collect_marks(main_marks_); }
     template <typename TA, typename TC>
     bool tgemm(const TA* A, int lda, const TA* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e) {
         mark_begin();
@@ -312,13 +327,57 @@ public:
     }
 
     // ------------------------------------------------------------------ K5 + K6
-    bool decode(const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
-                std::vector<SampleResult>& results, float* logits_host) override {
+    // One decode lane: a stream with its own activations, staging and timing context.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        float* x = nullptr;
+        T *y = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *ys = nullptr;
+        float* logits = nullptr;
+        float* partial = nullptr;
+        int* sched = nullptr;             // 2 x (work, exit) counters of the streaming cross-attention kernel: consecutive
+        unsigned cross_seq = 0;           // launches alternate, a launch may start its prologue while the previous one drains
+        char* pin = nullptr; size_t pin_cap = 0;
+        char* scratch = nullptr; size_t scratch_cap = 0;
+        Marks tm;
+        bool inflight = false, has_events = false;
+        // the chunk left in flight by decode_submit
+        int pend_S = 0; size_t pend_off = 0; size_t pend_pin_off = 0;
+        std::vector<SampleResult> results;
+        int last_logit_rows = 0;
+        std::chrono::steady_clock::time_point t_submit;
+    };
+    int n_lanes() const override { return (int)lanes_.size(); }
+
+    bool lane_pin(Lane& L, size_t bytes) {
+        if (bytes <= L.pin_cap) return true;
+        if (L.pin) { CUDA_OK(cudaStreamSynchronize(L.stream)); CUDA_OK(cudaFreeHost(L.pin)); L.pin = nullptr; }
+        L.pin_cap = align_up(bytes * 2, 1 << 16);
+        CUDA_OK(cudaMallocHost(&L.pin, L.pin_cap));
+        return true;
+    }
+    bool lane_scratch(Lane& L, size_t bytes) {
+        if (bytes <= L.scratch_cap) return true;
+        if (L.scratch) { CUDA_OK(cudaStreamSynchronize(L.stream)); CUDA_OK(cudaFree(L.scratch)); L.scratch = nullptr; }
+        L.scratch_cap = align_up(bytes * 2, 1 << 16);
+        CUDA_OK(cudaMalloc(&L.scratch, L.scratch_cap));
+        return true;
+    }
+
+    bool decode_submit(int lane, const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
+                       float* logits_host) override {
         CUDA_OK(cudaSetDevice(device_));
-        results.resize(sample_rows.size());
-        if (rows.empty()) return true;
+        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "decode: no such lane"; return false; }
+        Lane& L = lanes_[lane];
+        if (L.inflight) { err_ = "decode: lane is busy"; return false; }
         if (sp.size() != sample_rows.size()) { err_ = "decode: params/sample size mismatch"; return false; }
-        CUDA_OK(cudaEventRecord(ev_[0], stream_));
+        L.results.assign(sample_rows.size(), SampleResult{});
+        L.pend_S = 0;
+        L.inflight = true;
+        L.t_submit = std::chrono::steady_clock::now();
+        L.has_events = !rows.empty();
+        if (rows.empty()) return true;
+        CUDA_OK(cudaEventRecord(L.ev[0], L.stream));
         size_t si = 0;
         for (size_t r0 = 0; r0 < rows.size();) {
             // a chunk holds at most dec_rows_ rows and dec_samples_ sample rows
@@ -328,98 +387,147 @@ public:
                 if (sj - si == (size_t)dec_samples_) { r1 = (size_t)sample_rows[sj]; break; }
                 ++sj;
             }
-            if (r1 == r0) { err_ = "decode: cannot make progress"; return false; }
-            if (!decode_chunk(rows.data() + r0, (int)(r1 - r0), sample_rows.data() + si, (int)(sj - si), (int)r0, sp.data() + si,
-                              results.data() + si, logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr))
-                return false;
+            if (r1 == r0) { err_ = "decode: cannot make progress"; L.inflight = false; return false; }
+            const bool last = r1 == rows.size();
+            if (!decode_chunk(L, rows.data() + r0, (int)(r1 - r0), sample_rows.data() + si, (int)(sj - si), (int)r0, sp.data() + si, si,
+                              logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr)) { L.inflight = false; return false; }
+            if (!last && !finish_chunk(L)) { L.inflight = false; return false; }
             si = sj;
             r0 = r1;
         }
-        CUDA_OK(cudaEventRecord(ev_[1], stream_));
-        CUDA_OK(cudaStreamSynchronize(stream_));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
-        stats.ms_decode += ms;
-        collect_marks();
+        CUDA_OK(cudaEventRecord(L.ev[1], L.stream));
+        return true;
+    }
+
+    bool decode_collect(int lane, std::vector<SampleResult>& results) override {
+        CUDA_OK(cudaSetDevice(device_));
+        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "decode: no such lane"; return false; }
+        Lane& L = lanes_[lane];
+        if (!L.inflight) { err_ = "decode: nothing in flight on this lane"; return false; }
+        L.inflight = false;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!finish_chunk(L)) return false;
+        host_wait_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (L.has_events) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]) == cudaSuccess) stats.ms_decode += ms;
+        }
+        collect_marks(L.tm);
+        results = L.results;
+        return true;
+    }
+
+    // wait for the chunk in flight on a lane and take its sample results
+    bool finish_chunk(Lane& L) {
+        CUDA_OK(cudaStreamSynchronize(L.stream));
+        CUDA_OK(cudaGetLastError());
+        if (L.pend_S > 0) memcpy(L.results.data() + L.pend_off, L.pin + L.pend_pin_off, sizeof(SampleResult) * L.pend_S);
+        L.pend_S = 0;
         return true;
     }
 
     // Decoder layers for a step batch of R <= 128 token rows (bf16): every projection is a swap-AB split-K
     // tcgen05 GEMM that streams its weights through all SMs, finished by one fused epilogue kernel
     // (bias / GELU / residual / next LayerNorm / KV scatter).  14 launches per layer.
-    bool decode_layers_skinny(const RowDesc* drows, int R) {
+    bool decode_layers_skinny(Lane& Ln, const RowDesc* drows, int R) {
         const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        cudaStream_t st = Ln.stream;
         const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
         const size_t self_slot = (size_t)Ld * 2 * self_kv;
         const size_t cross_head = (size_t)kWinRows * 64, cross_kv = (size_t)kWinRows * d;
         const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
-        const bf16* y = reinterpret_cast<const bf16*>(d_y_);
+        const bf16* y = reinterpret_cast<const bf16*>(Ln.y);
         auto proj = [&](const void* X, int K, const T* W, int N, SkinnyEpilogue& e) -> bool {
             int splits = 0;
-            dmark_begin();
-            if (!launch_gemm_skinny_bf16_sm100(reinterpret_cast<const bf16*>(X), K, reinterpret_cast<const bf16*>(W), K, d_partial_, R, N, K, &splits,
-                                               stream_))
+            mark_begin(Ln.tm, detail_);
+            if (!launch_gemm_skinny_bf16_sm100(reinterpret_cast<const bf16*>(X), K, reinterpret_cast<const bf16*>(W), K, Ln.partial, R, N, K, &splits, st))
                 return gemm_fail();
-            dmark_end(10);
-            e.partial = d_partial_; e.splits = splits; e.R = R; e.N = N;
-            dmark_begin();
-            launch_skinny_reduce<T>(e, stream_);
-            dmark_end(11);
+            mark_end(Ln.tm, detail_, 10);
+            e.partial = Ln.partial; e.splits = splits; e.R = R; e.N = N;
+            mark_begin(Ln.tm, detail_);
+            launch_skinny_reduce<T>(e, st);
+            mark_end(Ln.tm, detail_, 11);
             return true;
         };
-        launch_layernorm<T>(d_x_, d, dec_[0].ln1_g, dec_[0].ln1_b, d_y_, d, R, d, stream_);
+        launch_layernorm<T>(Ln.x, d, dec_[0].ln1_g, dec_[0].ln1_b, Ln.y, d, R, d, st);
         for (int l = 0; l < Ld; ++l) {
             const Layer<T>& L = dec_[l];
             T* kc = self_pool_ + (size_t)l * 2 * self_kv;
             T* vc = kc + self_kv;
             {   // QKV projection + KV-cache append
                 SkinnyEpilogue e;
-                e.bias = L.bqkv; e.out = d_qkv_; e.out_ld = 3 * d;
+                e.bias = L.bqkv; e.out = Ln.qkv; e.out_ld = 3 * d;
                 e.rows = drows; e.kpanel = kc; e.vpanel = vc; e.slot_stride = self_slot; e.n_pos_cap = ntc; e.d = d;
                 if (!proj(y, d, L.wqkv, 3 * d, e)) return false;
             }
-            dmark_begin();
-            launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
-            dmark_end(12);
+            mark_begin(Ln.tm, detail_);
+            launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
+            mark_end(Ln.tm, detail_, 12);
             {   // out projection + residual + cross-attention LayerNorm
                 SkinnyEpilogue e;
-                e.bias = L.bo; e.x = d_x_; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = d_y_;
-                if (!proj(d_att_, d, L.wo, d, e)) return false;
+                e.bias = L.bo; e.x = Ln.x; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = Ln.y;
+                if (!proj(Ln.att, d, L.wo, d, e)) return false;
             }
             {   // cross-attention query
                 SkinnyEpilogue e;
-                e.bias = L.bcq; e.out = d_qkv_; e.out_ld = d;
+                e.bias = L.bcq; e.out = Ln.qkv; e.out_ld = d;
                 if (!proj(y, d, L.wcq, d, e)) return false;
             }
             const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
             const T* cv = ck + cross_kv;
             const bool timed = profiling && (l % kCrossSample) == 0;
-            if (timed) mark_begin(); else dmark_begin();
-            launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
-            if (timed) { mark_end(2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else dmark_end(13);
+            mark_begin(Ln.tm, timed || detail_);
+            if (!cross_attention(Ln, drows, R, Ln.qkv, d, ck, cv, Ln.att, cross_slot, cross_head)) return false;
+            if (timed) { mark_end(Ln.tm, true, 2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out projection + residual + MLP LayerNorm
                 SkinnyEpilogue e;
-                e.bias = L.bco; e.x = d_x_; e.ln_g = L.ln2_g; e.ln_b = L.ln2_b; e.y = d_y_;
-                if (!proj(d_att_, d, L.wco, d, e)) return false;
+                e.bias = L.bco; e.x = Ln.x; e.ln_g = L.ln2_g; e.ln_b = L.ln2_b; e.y = Ln.y;
+                if (!proj(Ln.att, d, L.wco, d, e)) return false;
             }
             {   // FC1 + GELU
                 SkinnyEpilogue e;
-                e.bias = L.b1; e.act = 1; e.out = d_h_; e.out_ld = 4 * d;
+                e.bias = L.b1; e.act = 1; e.out = Ln.h; e.out_ld = 4 * d;
                 if (!proj(y, d, L.w1, 4 * d, e)) return false;
             }
             {   // FC2 + residual + the next layer's first LayerNorm
                 SkinnyEpilogue e;
-                e.bias = L.b2; e.x = d_x_;
-                if (l + 1 < Ld) { e.ln_g = dec_[l + 1].ln1_g; e.ln_b = dec_[l + 1].ln1_b; e.y = d_y_; }
-                if (!proj(d_h_, 4 * d, L.w2, d, e)) return false;
+                e.bias = L.b2; e.x = Ln.x;
+                if (l + 1 < Ld) { e.ln_g = dec_[l + 1].ln1_g; e.ln_b = dec_[l + 1].ln1_b; e.y = Ln.y; }
+                if (!proj(Ln.h, 4 * d, L.w2, d, e)) return false;
             }
         }
         return true;
     }
 
-    bool decode_chunk(const RowDesc* rows, int R, const int* samp, int S, int row_base, const SampleParams* sp, SampleResult* res,
+    // cross-attention of R single-token rows over the head-major cross-KV panels of one layer
+    bool cross_attention(Lane& Ln, const RowDesc* drows, int R, const float* q, int ldq, const float* ck, const float* cv, float* out, size_t cross_slot,
+                         size_t cross_head) {
+        launch_dec_attention<float>(drows, R, q, ldq, ck, cv, out, d_, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, Ln.stream);
+        return true;
+    }
+    bool cross_attention(Lane& Ln, const RowDesc* drows, int R, const bf16* q, int ldq, const bf16* ck, const bf16* cv, bf16* out, size_t cross_slot,
+                         size_t cross_head) {
+        if (cross_mode_ == 0) {
+            launch_dec_attention<bf16>(drows, R, q, ldq, ck, cv, out, d_, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, Ln.stream);
+            return true;
+        }
+        if (cross_mode_ == 1) {
+            if (!launch_dec_cross_attention_sm100(drows, R, q, ldq, ck, cv, out, d_, hp_.n_text_head, cross_slot, cross_head, hp_.n_audio_ctx, cross_ctas_, Ln.stream))
+                return gemm_fail();
+            return true;
+        }
+        if (!launch_dec_cross_attention_tc_sm100(drows, R, q, ldq, cross_pool_, (size_t)audio_cap_ * cross_slot, (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_),
+                                                 out, d_, hp_.n_text_head, cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, Ln.stream))
+            return gemm_fail();
+        return true;
+    }
+
+    // Queues one chunk of rows on the lane; its sample results land in the lane's pinned staging
+    // (finish_chunk picks them up after the stream has drained).
+    bool decode_chunk(Lane& Ln, const RowDesc* rows, int R, const int* samp, int S, int row_base, const SampleParams* sp, size_t res_off,
                       float* logits_host) {
         const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        cudaStream_t st = Ln.stream;
         for (int r = 0; r < R; ++r) {
             const RowDesc& rd = rows[r];
             if (rd.token < 0 || rd.token >= hp_.n_vocab || rd.pos < 0 || rd.pos >= ntc || rd.kv_slot < 0 || rd.kv_slot >= kv_cap_ ||
@@ -427,22 +535,21 @@ public:
         }
         const size_t rows_bytes = align_up(sizeof(RowDesc) * R, 256), idx_bytes = align_up(sizeof(int) * std::max(S, 1), 256);
         const size_t sp_bytes = align_up(sizeof(SampleParams) * std::max(S, 1), 256), res_bytes = align_up(sizeof(SampleResult) * std::max(S, 1), 256);
-        if (!ensure_pin(rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
-        if (!ensure_dev_scratch(rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
-        CUDA_OK(cudaStreamSynchronize(stream_));  // pinned staging reuse
-        char* hp = pin_;
+        if (!lane_pin(Ln, rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
+        if (!lane_scratch(Ln, rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
+        char* hp = Ln.pin;
         memcpy(hp, rows, sizeof(RowDesc) * R);
         int* hidx = reinterpret_cast<int*>(hp + rows_bytes);
         for (int i = 0; i < S; ++i) hidx[i] = samp[i] - row_base;
         if (S) memcpy(hp + rows_bytes + idx_bytes, sp, sizeof(SampleParams) * S);
-        CUDA_OK(cudaMemcpyAsync(dev_scratch_, hp, rows_bytes + idx_bytes + sp_bytes, cudaMemcpyHostToDevice, stream_));
-        const RowDesc* drows = reinterpret_cast<const RowDesc*>(dev_scratch_);
-        const int* didx = reinterpret_cast<const int*>(dev_scratch_ + rows_bytes);
-        const SampleParams* dsp = reinterpret_cast<const SampleParams*>(dev_scratch_ + rows_bytes + idx_bytes);
-        SampleResult* dres = reinterpret_cast<SampleResult*>(dev_scratch_ + rows_bytes + idx_bytes + sp_bytes);
+        CUDA_OK(cudaMemcpyAsync(Ln.scratch, hp, rows_bytes + idx_bytes + sp_bytes, cudaMemcpyHostToDevice, st));
+        const RowDesc* drows = reinterpret_cast<const RowDesc*>(Ln.scratch);
+        const int* didx = reinterpret_cast<const int*>(Ln.scratch + rows_bytes);
+        const SampleParams* dsp = reinterpret_cast<const SampleParams*>(Ln.scratch + rows_bytes + idx_bytes);
+        SampleResult* dres = reinterpret_cast<SampleResult*>(Ln.scratch + rows_bytes + idx_bytes + sp_bytes);
 
         const auto host_t0 = std::chrono::steady_clock::now();
-        launch_embed<T>(drows, R, tok_emb_, dec_pos_, d_x_, d, stream_);
+        launch_embed<T>(drows, R, tok_emb_, dec_pos_, Ln.x, d, st);
         // head-major KV panels: self [slot][layer][K|V][head][448][64], cross [slot][layer][K|V][head][1536][64]
         const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
         const size_t self_slot = (size_t)Ld * 2 * self_kv;
@@ -450,79 +557,83 @@ public:
         const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
         const bool skinny = use_skinny_ && sizeof(T) == 2 && R <= 128 && 4 * d <= 5120;
         if (skinny) {
-            if (!decode_layers_skinny(drows, R)) return false;
+            if (!decode_layers_skinny(Ln, drows, R)) return false;
         } else {
             for (int l = 0; l < Ld; ++l) {
                 const Layer<T>& L = dec_[l];
-                launch_layernorm<T>(d_x_, d, L.ln1_g, L.ln1_b, d_y_, d, R, d, stream_);
-                { Epilogue e; e.bias = L.bqkv; if (!gemm(d_y_, d, L.wqkv, d, d_qkv_, 3 * d, R, 3 * d, d, e, stream_)) return gemm_fail(); }
+                launch_layernorm<T>(Ln.x, d, L.ln1_g, L.ln1_b, Ln.y, d, R, d, st);
+                { Epilogue e; e.bias = L.bqkv; if (!gemm(Ln.y, d, L.wqkv, d, Ln.qkv, 3 * d, R, 3 * d, d, e, st)) return gemm_fail(); }
                 T* kc = self_pool_ + (size_t)l * 2 * self_kv;
                 T* vc = kc + self_kv;
-                launch_scatter_kv<T>(drows, R, d_qkv_, kc, vc, self_slot, ntc, d, stream_);
-                launch_dec_attention<T>(drows, R, d_qkv_, 3 * d, kc, vc, d_att_, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, stream_);
-                { Epilogue e; e.bias = L.bo; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wo, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
-                launch_layernorm<T>(d_x_, d, L.lnc_g, L.lnc_b, d_y_, d, R, d, stream_);
-                { Epilogue e; e.bias = L.bcq; if (!gemm(d_y_, d, L.wcq, d, d_qkv_, d, R, d, d, e, stream_)) return gemm_fail(); }
+                launch_scatter_kv<T>(drows, R, Ln.qkv, kc, vc, self_slot, ntc, d, st);
+                launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
+                { Epilogue e; e.bias = L.bo; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.att, d, L.wo, d, Ln.x, d, R, d, d, e, st)) return gemm_fail(); }
+                launch_layernorm<T>(Ln.x, d, L.lnc_g, L.lnc_b, Ln.y, d, R, d, st);
+                { Epilogue e; e.bias = L.bcq; if (!gemm(Ln.y, d, L.wcq, d, Ln.qkv, d, R, d, d, e, st)) return gemm_fail(); }
                 const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
                 const T* cv = ck + cross_kv;
-                mark_begin();
-                launch_dec_attention<T>(drows, R, d_qkv_, d, ck, cv, d_att_, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, stream_);
-                mark_end(2);
+                mark_begin(Ln.tm, profiling);
+                launch_dec_attention<T>(drows, R, Ln.qkv, d, ck, cv, Ln.att, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, st);
+                mark_end(Ln.tm, profiling, 2);
                 if (profiling) stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T);
-                { Epilogue e; e.bias = L.bco; e.res = d_x_; e.res_ld = d; if (!gemm(d_att_, d, L.wco, d, d_x_, d, R, d, d, e, stream_)) return gemm_fail(); }
-                launch_layernorm<T>(d_x_, d, L.ln2_g, L.ln2_b, d_y_, d, R, d, stream_);
-                { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(d_y_, d, L.w1, d, d_h_, 4 * d, R, 4 * d, d, e, stream_)) return gemm_fail(); }
-                { Epilogue e; e.bias = L.b2; e.res = d_x_; e.res_ld = d; if (!gemm(d_h_, 4 * d, L.w2, 4 * d, d_x_, d, R, d, 4 * d, e, stream_)) return gemm_fail(); }
+                { Epilogue e; e.bias = L.bco; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.att, d, L.wco, d, Ln.x, d, R, d, d, e, st)) return gemm_fail(); }
+                launch_layernorm<T>(Ln.x, d, L.ln2_g, L.ln2_b, Ln.y, d, R, d, st);
+                { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(Ln.y, d, L.w1, d, Ln.h, 4 * d, R, 4 * d, d, e, st)) return gemm_fail(); }
+                { Epilogue e; e.bias = L.b2; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.h, 4 * d, L.w2, 4 * d, Ln.x, d, R, d, 4 * d, e, st)) return gemm_fail(); }
             }
         }
+        Ln.pend_S = 0;
         if (S > 0) {
-            dmark_begin();
-            launch_layernorm_gather<T>(d_x_, d, didx, dec_ln_g_, dec_ln_b_, d_ys_, d, S, d, stream_);
-            { Epilogue e; if (!gemm(d_ys_, d, tok_emb_, d, d_logits_, hp_.n_vocab, S, hp_.n_vocab, d, e, stream_)) return gemm_fail(); }
-            launch_process_logits(d_logits_, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, nullptr, stream_);
-            dmark_end(15);
-            CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, stream_));
+            mark_begin(Ln.tm, detail_);
+            launch_layernorm_gather<T>(Ln.x, d, didx, dec_ln_g_, dec_ln_b_, Ln.ys, d, S, d, st);
+            { Epilogue e; if (!gemm(Ln.ys, d, tok_emb_, d, Ln.logits, hp_.n_vocab, S, hp_.n_vocab, d, e, st)) return gemm_fail(); }
+            launch_process_logits(Ln.logits, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, nullptr, st);
+            mark_end(Ln.tm, detail_, 15);
+            CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, st));
             if (logits_host)
-                CUDA_OK(cudaMemcpyAsync(logits_host, d_logits_, sizeof(float) * (size_t)S * hp_.n_vocab, cudaMemcpyDeviceToHost, stream_));
+                CUDA_OK(cudaMemcpyAsync(logits_host, Ln.logits, sizeof(float) * (size_t)S * hp_.n_vocab, cudaMemcpyDeviceToHost, st));
+            Ln.pend_S = S;
+            Ln.pend_off = res_off;
+            Ln.pend_pin_off = rows_bytes + idx_bytes + sp_bytes;
         }
-        const auto host_t1 = std::chrono::steady_clock::now();
-        CUDA_OK(cudaStreamSynchronize(stream_));
-        const auto host_t2 = std::chrono::steady_clock::now();
-        host_issue_ms_ += std::chrono::duration<double, std::milli>(host_t1 - host_t0).count();
-        host_wait_ms_ += std::chrono::duration<double, std::milli>(host_t2 - host_t1).count();
-        CUDA_OK(cudaGetLastError());
-        if (S > 0) memcpy(res, hp + rows_bytes + idx_bytes + sp_bytes, sizeof(SampleResult) * S);
-        last_logit_rows_ = S;
+        host_issue_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        Ln.last_logit_rows = S;
         return true;
     }
 
-    bool lang_probs(int sample_index, float* probs_host, int* best) override {
+    bool lang_probs(int lane, int sample_index, float* probs_host, int* best) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (sample_index < 0 || sample_index >= last_logit_rows_) { err_ = "lang_probs: no such logits row"; return false; }
-        if (!ensure_dev_scratch(1024)) return false;
-        float* dp = reinterpret_cast<float*>(dev_scratch_);
-        int* db = reinterpret_cast<int*>(dev_scratch_ + 512);
-        launch_lang_probs(d_logits_ + (size_t)sample_index * hp_.n_vocab, vocab_ids, dp, db, stream_);
+        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "lang_probs: no such lane"; return false; }
+        Lane& L = lanes_[lane];
+        if (L.inflight || sample_index < 0 || sample_index >= L.last_logit_rows) { err_ = "lang_probs: no such logits row"; return false; }
+        CUDA_OK(cudaStreamSynchronize(L.stream));
+        if (!lane_scratch(L, 1024)) return false;
+        float* dp = reinterpret_cast<float*>(L.scratch);
+        int* db = reinterpret_cast<int*>(L.scratch + 512);
+        launch_lang_probs(L.logits + (size_t)sample_index * hp_.n_vocab, vocab_ids, dp, db, L.stream);
         float hp[kNumLangs];
-        CUDA_OK(cudaMemcpyAsync(hp, dp, sizeof(hp), cudaMemcpyDeviceToHost, stream_));
-        CUDA_OK(cudaMemcpyAsync(best, db, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaMemcpyAsync(hp, dp, sizeof(hp), cudaMemcpyDeviceToHost, L.stream));
+        CUDA_OK(cudaMemcpyAsync(best, db, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+        CUDA_OK(cudaStreamSynchronize(L.stream));
         if (probs_host) memcpy(probs_host, hp, sizeof(hp));
         return true;
     }
 
-    bool kv_copy(const std::vector<KvCopy>& pairs) override {
+    bool kv_copy(int lane, const std::vector<KvCopy>& pairs) override {
         CUDA_OK(cudaSetDevice(device_));
         if (pairs.empty()) return true;
+        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "kv_copy: no such lane"; return false; }
+        Lane& L = lanes_[lane];
+        if (L.inflight) { err_ = "kv_copy: lane is busy"; return false; }
         const size_t bytes = sizeof(KvCopy) * pairs.size();
-        if (!ensure_pin(bytes) || !ensure_dev_scratch(bytes)) return false;
-        CUDA_OK(cudaStreamSynchronize(stream_));
-        memcpy(pin_, pairs.data(), bytes);
-        CUDA_OK(cudaMemcpyAsync(dev_scratch_, pin_, bytes, cudaMemcpyHostToDevice, stream_));
+        if (!lane_pin(L, bytes) || !lane_scratch(L, bytes)) return false;
+        CUDA_OK(cudaStreamSynchronize(L.stream));
+        memcpy(L.pin, pairs.data(), bytes);
+        CUDA_OK(cudaMemcpyAsync(L.scratch, L.pin, bytes, cudaMemcpyHostToDevice, L.stream));
         const int d = d_, ntc = hp_.n_text_ctx, Ld = hp_.n_text_layer;
-        launch_kv_copy<T>(reinterpret_cast<const KvCopy*>(dev_scratch_), (int)pairs.size(), self_pool_, (size_t)Ld * 2 * ntc * d,
-                          2 * Ld * hp_.n_text_head, (size_t)ntc * 64, stream_);
-        CUDA_OK(cudaStreamSynchronize(stream_));
+        launch_kv_copy<T>(reinterpret_cast<const KvCopy*>(L.scratch), (int)pairs.size(), self_pool_, (size_t)Ld * 2 * ntc * d,
+                          2 * Ld * hp_.n_text_head, (size_t)ntc * 64, L.stream);
+        CUDA_OK(cudaStreamSynchronize(L.stream));
         return true;
     }
 
@@ -637,7 +748,7 @@ private:
     template <typename P>
     bool grow_pool(P*& pool, int old_cap, int new_cap, size_t slot_elems) {
         P* np = nullptr;
-        CUDA_OK(cudaStreamSynchronize(stream_));
+        CUDA_OK(cudaDeviceSynchronize());  // every lane may be reading the pool
         CUDA_OK(cudaMalloc(&np, (size_t)new_cap * slot_elems * sizeof(P)));
         if (pool && old_cap > 0) CUDA_OK(cudaMemcpy(np, pool, (size_t)old_cap * slot_elems * sizeof(P), cudaMemcpyDeviceToDevice));
         if (pool) CUDA_OK(cudaFree(pool));
@@ -837,8 +948,11 @@ private:
         dec_samples_ = std::max(8, env_int("NOBS_WHISPER_DEC_SAMPLES", 1024));
         use_skinny_ = env_int("NOBS_WHISPER_SKINNY", 1) != 0;
         detail_ = env_int("NOBS_WHISPER_PROFILE_DECODE", 0) != 0;
-        // encoder and decoder never run concurrently: both views alias one arena
-        Arena e;
+        cross_mode_ = env_int("NOBS_WHISPER_CROSS_MODE", 2);
+        cross_ctas_ = env_int("NOBS_WHISPER_CROSS_CTAS", 0);
+        const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 2)));
+        // The encoder and every decode lane own their activations: a lane may decode while the encoder
+        // works on other windows and while other lanes decode.
         auto plan_enc = [&](Arena& a) {
             const size_t M = (size_t)enc_batch_ * kWinRows;
             e_mel_ = (T*)a.take(((size_t)enc_batch_ * kWinRowsIn + 2) * nm * sizeof(T));
@@ -849,37 +963,43 @@ private:
             e_att_ = (T*)a.take(M * d * sizeof(T));
             e_h_ = (T*)a.take(M * 4 * d * sizeof(T));
         };
-        auto plan_dec = [&](Arena& a) {
+        auto plan_dec = [&](Arena& a, Lane& L) {
             const size_t R = dec_rows_, S = dec_samples_;
-            d_x_ = (float*)a.take(R * d * sizeof(float));
-            d_y_ = (T*)a.take(R * d * sizeof(T));
-            d_qkv_ = (T*)a.take(R * 3 * d * sizeof(T));
-            d_att_ = (T*)a.take(R * d * sizeof(T));
-            d_h_ = (T*)a.take(R * 4 * d * sizeof(T));
-            d_partial_ = (float*)a.take((size_t)16 << 20);  // skinny-GEMM split-K partials: <= 4 splits x 128 rows x 5120 cols (FC1) fp32
-            d_ys_ = (T*)a.take(S * d * sizeof(T));
-            d_logits_ = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
+            L.x = (float*)a.take(R * d * sizeof(float));
+            L.y = (T*)a.take(R * d * sizeof(T));
+            L.qkv = (T*)a.take(R * 3 * d * sizeof(T));
+            L.att = (T*)a.take(R * d * sizeof(T));
+            L.h = (T*)a.take(R * 4 * d * sizeof(T));
+            L.partial = (float*)a.take((size_t)16 << 20);  // skinny-GEMM split-K partials: <= 4 splits x 128 rows x 5120 cols (FC1) fp32
+            L.sched = (int*)a.take(256);
+            L.ys = (T*)a.take(S * d * sizeof(T));
+            L.logits = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
         };
-        Arena se, sd;
-        plan_enc(se);
-        plan_dec(sd);
-        const size_t bytes = std::max(se.used, sd.used) + 512;
+        lanes_.assign(n_lanes, Lane());
+        Arena sizing;
+        plan_enc(sizing);
+        for (auto& L : lanes_) plan_dec(sizing, L);
+        const size_t bytes = sizing.used + 512;
         char* base = nullptr;
         CUDA_OK(cudaMalloc(&base, bytes));
         owned_.push_back(base);
         CUDA_OK(cudaMemset(base, 0, bytes));
-        Arena ae; ae.base = base; ae.cap = bytes;
-        Arena ad = ae;
-        plan_enc(ae);
-        plan_dec(ad);
+        Arena a; a.base = base; a.cap = bytes;
+        plan_enc(a);
+        for (auto& L : lanes_) {
+            plan_dec(a, L);
+            CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            for (auto& e : L.ev) CUDA_OK(cudaEventCreate(&e));
+            L.tm.s = L.stream;
+        }
+        main_marks_.s = stream_;
         ws_base_ = base;
         ws_bytes_ = bytes;
         return true;
     }
 
-    // the conv operands rely on zero rows that only the encoder view keeps zero: rows 0 / last
-    // of e_mel_ and row 0 of e_h1_.  The decoder view aliases the same memory, so they are
-    // re-zeroed at the start of every encode batch.
+    // the conv operands rely on zero rows: rows 0 / last of e_mel_ (the last one moves with the batch size)
+    // and row 0 of e_h1_; they are re-zeroed at the start of every encode batch.
 public:
     bool rezero_conv_pads(int nb) {
         const int d = d_, nm = hp_.n_mels;
@@ -918,22 +1038,18 @@ private:
     size_t ws_bytes_ = 0;
     T *e_mel_ = nullptr, *e_h1_ = nullptr, *e_y_ = nullptr, *e_qkv_ = nullptr, *e_att_ = nullptr, *e_h_ = nullptr;
     float* e_x_ = nullptr;
-    float* d_x_ = nullptr;
-    T *d_y_ = nullptr, *d_qkv_ = nullptr, *d_att_ = nullptr, *d_h_ = nullptr, *d_ys_ = nullptr;
-    float* d_logits_ = nullptr;
-    float* d_partial_ = nullptr;
+    std::vector<Lane> lanes_;
+    Marks main_marks_;
     bool use_skinny_ = true;
+    int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
+    int cross_ctas_ = 0;              // > 0: cap that kernel's grid
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
     double host_issue_ms_ = 0, host_wait_ms_ = 0;  // decode_chunk: time spent issuing launches vs waiting for the GPU
     double detail_ms_[8] = {};
     long detail_n_[8] = {};
     static constexpr int kCrossSample = 8;  // profiling: time the cross-attention of every 8th layer
-    int last_logit_rows_ = 0;
 
     cudaEvent_t user_ev_[8] = {};
-    std::vector<cudaEvent_t> ev_pool_;
-    size_t ev_used_ = 0;
-    std::vector<std::pair<int, int>> marks_;
     char* pin_ = nullptr;
     size_t pin_cap_ = 0;
     char* dev_scratch_ = nullptr;

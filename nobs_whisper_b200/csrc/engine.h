@@ -80,13 +80,23 @@ public:
 
     virtual bool compute_mel(const std::vector<MelRequest>& reqs) = 0;
     virtual bool encode(const std::vector<EncodeRequest>& reqs) = 0;
-    // rows: token rows in order; sample_rows[i] indexes `rows`; one SampleParams/SampleResult per sample row.
-    // logits_host (optional): receives [n_sample][n_vocab] raw logits.
-    virtual bool decode(const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
-                        std::vector<SampleResult>& results, float* logits_host) = 0;
-    // language probabilities from the raw logits of sample row `i` of the last decode()
-    virtual bool lang_probs(int sample_index, float* probs_host /*[100] or null*/, int* best) = 0;
-    virtual bool kv_copy(const std::vector<KvCopy>& pairs) = 0;
+    // Decode lanes: independent (stream, workspace) pairs.  Jobs are partitioned over lanes by the host driver;
+    // while one lane streams its cross-KV panels (HBM-bound) the projection chain of another lane
+    // (latency-bound) runs on the same SMs, and the host prepares one lane's next round while the others compute.
+    virtual int n_lanes() const = 0;
+    // rows: token rows in order; sample_rows[i] indexes `rows`; one SampleParams per sample row.
+    // logits_host (optional): receives [n_sample][n_vocab] raw logits.  Returns once the work is queued.
+    virtual bool decode_submit(int lane, const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
+                               float* logits_host) = 0;
+    // waits for the lane's round; one SampleResult per sample row
+    virtual bool decode_collect(int lane, std::vector<SampleResult>& results) = 0;
+    bool decode(const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
+                std::vector<SampleResult>& results, float* logits_host) {
+        return decode_submit(0, rows, sample_rows, sp, logits_host) && decode_collect(0, results);
+    }
+    // language probabilities from the raw logits of sample row `i` of the lane's last round
+    virtual bool lang_probs(int lane, int sample_index, float* probs_host /*[100] or null*/, int* best) = 0;
+    virtual bool kv_copy(int lane, const std::vector<KvCopy>& pairs) = 0;
     // stage-parity hook: run K6 on host-supplied logits
     virtual bool process_logits_host(const float* logits, const SampleParams& sp, SampleResult& out, float* logprobs, float* probs) = 0;
 

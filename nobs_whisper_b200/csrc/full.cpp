@@ -52,6 +52,7 @@ struct Job {
     std::vector<whisper_token> prompt, prompt_init;
     Dec dec[WHISPER_MAX_DECODERS];
     int best = 0;
+    int lane = 0;  // decode lane this audio belongs to
     // bookkeeping of the round in flight
     int first_sample = -1, n_samples = 0;
     std::vector<int> live;  // decoder index of each sample of this round
@@ -96,6 +97,16 @@ bool same_tokens(const Sequence& a, const Sequence& b) {
 }
 
 class Driver {
+    struct LaneState {           // host side of one engine decode lane
+        std::vector<int> jobs;   // indices into jobs_
+        std::vector<RowDesc> rows;
+        std::vector<int> samp;
+        std::vector<SampleParams> sp;
+        std::vector<SampleResult> res;
+        std::vector<KvCopy> kv_pairs_a, kv_pairs_b;
+        bool inflight = false;
+    };
+
 public:
     Driver(whisper_context* ctx) : ctx_(ctx), eng_(*ctx->engine), vocab_(ctx->model.vocab), hp_(ctx->model.hp) {}
 
@@ -133,25 +144,49 @@ public:
                 if (!ensure_state_slots(ctx_, j.st, kv_needed(j))) return fail_all(rc, n, -100);
             }
         }
-        // ---- rounds
+        // ---- decode lanes: contiguous blocks of live audios per lane (an audio never changes lane, so its KV
+        // slots are only ever touched by one stream)
+        {
+            std::vector<int> live;
+            for (int i = 0; i < n; ++i) if (jobs_[i].phase != Phase::Finished) live.push_back(i);
+            n_lanes_ = std::max(1, std::min(eng_.n_lanes(), (int)live.size()));
+            for (size_t k = 0; k < live.size(); ++k) jobs_[live[k]].lane = (int)(k * n_lanes_ / live.size());
+            lanes_.assign(n_lanes_, LaneState());
+            for (int i = 0; i < n; ++i) lanes_[jobs_[i].lane].jobs.push_back(i);
+        }
+        // ---- rounds: every lane alternates "collect results, advance its audios, queue the next round";
+        // while the host works on one lane the others keep the GPU busy.
         while (true) {
-            if (!encode_round()) return fail_all(rc, n, -6);
-            rows_.clear(); samp_.clear(); sp_.clear();
-            kv_pairs_a_.clear(); kv_pairs_b_.clear();
-            bool any = false;
-            for (auto& j : jobs_) any |= emit_rows(j);
-            if (!any) {
-                bool pending = false;
-                for (auto& j : jobs_) pending |= (j.phase == Phase::Window);
-                if (pending) continue;  // windows that still have to be encoded
-                break;
+            bool active = false;
+            for (int ln = 0; ln < n_lanes_; ++ln) {
+                LaneState& L = lanes_[ln];
+                if (L.inflight) {
+                    if (!eng_.decode_collect(ln, L.res)) return fail_all(rc, n, -8);
+                    L.inflight = false;
+                    for (int i : L.jobs) consume(jobs_[i]);
+                    if (!L.kv_pairs_a.empty()) {
+                        if (!eng_.kv_copy(ln, L.kv_pairs_a)) return fail_all(rc, n, -8);
+                        if (!L.kv_pairs_b.empty() && !eng_.kv_copy(ln, L.kv_pairs_b)) return fail_all(rc, n, -8);
+                    }
+                }
+                while (true) {
+                    if (!encode_round(L)) return fail_all(rc, n, -6);
+                    L.rows.clear(); L.samp.clear(); L.sp.clear();
+                    L.kv_pairs_a.clear(); L.kv_pairs_b.clear();
+                    bool any = false;
+                    for (int i : L.jobs) any |= emit_rows(jobs_[i]);
+                    if (any) {
+                        if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr)) return fail_all(rc, n, -8);
+                        L.inflight = true;
+                        active = true;
+                        break;
+                    }
+                    bool pending = false;
+                    for (int i : L.jobs) pending |= (jobs_[i].phase == Phase::Window);
+                    if (!pending) break;  // otherwise: windows that still have to be encoded
+                }
             }
-            if (!eng_.decode(rows_, samp_, sp_, res_, nullptr)) return fail_all(rc, n, -8);
-            for (auto& j : jobs_) consume(j);
-            if (!kv_pairs_a_.empty()) {
-                if (!eng_.kv_copy(kv_pairs_a_)) return fail_all(rc, n, -8);
-                if (!kv_pairs_b_.empty() && !eng_.kv_copy(kv_pairs_b_)) return fail_all(rc, n, -8);
-            }
+            if (!active) break;
         }
         const long launches = kernel_launch_count() - launches0;
         for (int i = 0; i < n; ++i) {
@@ -238,9 +273,10 @@ private:
     }
 
     // Encode every window that is due (language-detect windows included), as one batch.
-    bool encode_round() {
+    bool encode_round(LaneState& L) {
         enc_.clear();
-        for (auto& j : jobs_) {
+        for (int ji : L.jobs) {
+            Job& j = jobs_[ji];
             if (j.phase == Phase::Window && j.seek + 100 >= j.seek_end) j.phase = Phase::Finished;  // under 1 s left
             if (j.phase != Phase::Window && j.phase != Phase::LangDetect) continue;
             const int seek = j.phase == Phase::LangDetect ? j.seek_start : j.seek;
@@ -289,6 +325,10 @@ private:
 
     // Append this job's rows for the next decoder round.  Returns false if it has none.
     bool emit_rows(Job& j) {
+        LaneState& L = lanes_[j.lane];
+        std::vector<RowDesc>& rows_ = L.rows;
+        std::vector<int>& samp_ = L.samp;
+        std::vector<SampleParams>& sp_ = L.sp;
         j.first_sample = (int)samp_.size();
         j.n_samples = 0;
         j.live.clear();
@@ -367,9 +407,12 @@ private:
     void consume(Job& j) {
         if (j.n_samples == 0) return;
         whisper_state* st = j.st;
+        LaneState& L = lanes_[j.lane];
+        const std::vector<SampleResult>& res_ = L.res;
+        std::vector<KvCopy>& kv_pairs_a_ = L.kv_pairs_a;
         if (j.phase == Phase::LangDetect) {
             int best = 0;
-            if (!eng_.lang_probs(j.first_sample, nullptr, &best)) { j.rc = -3; j.phase = Phase::Finished; return; }
+            if (!eng_.lang_probs(j.lane, j.first_sample, nullptr, &best)) { j.rc = -3; j.phase = Phase::Finished; return; }
             j.lang = lang_str(best);
             if (j.p.detect_language) { st->lang_id = best; j.phase = Phase::Finished; return; }
             j.phase = Phase::Window;
@@ -390,6 +433,8 @@ private:
     // One iteration of the reference's token loop, from "sample" to "all decoders finished?".
     void advance(Job& j) {
         whisper_state* st = j.st;
+        std::vector<KvCopy>& kv_pairs_a_ = lanes_[j.lane].kv_pairs_a;
+        std::vector<KvCopy>& kv_pairs_b_ = lanes_[j.lane].kv_pairs_b;
         const int i = j.step;
         const bool beam = j.p.strategy == WHISPER_SAMPLING_BEAM_SEARCH;
         if (!beam) {
@@ -548,11 +593,8 @@ private:
     const HParams& hp_;
     std::vector<Job> jobs_;
     std::vector<EncodeRequest> enc_;
-    std::vector<RowDesc> rows_;
-    std::vector<int> samp_;
-    std::vector<SampleParams> sp_;
-    std::vector<SampleResult> res_;
-    std::vector<KvCopy> kv_pairs_a_, kv_pairs_b_;
+    std::vector<LaneState> lanes_;
+    int n_lanes_ = 1;
 };
 
 }  // namespace

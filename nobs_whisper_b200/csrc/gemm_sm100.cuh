@@ -21,6 +21,13 @@ bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int 
 // one small CTA per SM fed by a cp.async.bulk ring (cross_attention_sm100.cu).  max_ctas > 0 caps the grid.
 bool launch_dec_cross_attention_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* kbase, const bf16* vbase, bf16* out, int ldo,
                                       int n_head, size_t slot_stride, size_t head_stride, int n_keys, int max_ctas, cudaStream_t s);
+// Tensor-core variant: panels go TMA -> 128B-swizzled shared memory -> tcgen05.mma (scores and P*V), the SM's
+// issue slots stay free for co-resident kernels.  `pool` is the whole cross-KV pool (pool_elems bf16), k_off / v_off
+// the element offsets of this layer's K / V panels inside an audio slot, head panels 1536 x 64 apart.  `sched`: two
+// zero-initialised device ints owned by the calling stream (work counter + exit counter; the kernel re-arms them).
+// Back-to-back launches on one stream must alternate between two such pairs (a launch's prologue may overlap its predecessor).
+bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
+                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s);
 const char* sm100_last_error();
 
 }  // namespace nobs

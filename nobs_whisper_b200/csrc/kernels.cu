@@ -770,86 +770,99 @@ template void launch_kv_copy<bf16>(const KvCopy*, int, bf16*, size_t, int, size_
 // ------------------------------------------------------------------------------------------
 // skinny-GEMM epilogue: one token row per block
 // ------------------------------------------------------------------------------------------
-constexpr int SR_THREADS = 256;
-constexpr int SR_MAXV = 20;  // N <= 5120
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&v)[4]) {   // p is 8-byte aligned
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
 
+constexpr int SR_THREADS = 256;
+constexpr int SR_MAXG = 5;   // float4 column groups per thread: N <= 5120
+constexpr int SR_PLANES = 8; // split-K planes summed per trip (independent 16-byte loads in flight)
+
+// Register budget matters here: this kernel has to share SMs with the persistent cross-attention CTAs of
+// another decode lane (2 x 288 threads x 64 registers), so it stays at <= 64 registers per thread.
 template <typename T>
-__global__ void __launch_bounds__(SR_THREADS) skinny_reduce_kernel(SkinnyEpilogue e) {
+__global__ void __launch_bounds__(SR_THREADS, 4) skinny_reduce_kernel(SkinnyEpilogue e) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x;
     const size_t plane = (size_t)e.R * e.N;
     const float* p = e.partial + (size_t)r * e.N;
-    float vals[SR_MAXV];
+    const int n4 = e.N >> 2;                      // N is a multiple of 4 (model widths are multiples of 64)
+    float4 vals[SR_MAXG];
     RowDesc rd{};
     if (e.rows) rd = e.rows[r];
-    // split-K sum, splits outermost: every iteration issues all of this thread's (independent) loads
-    // back to back instead of one dependent L2 round trip per addend
-#pragma unroll
-    for (int i = 0; i < SR_MAXV; ++i) vals[i] = 0.0f;
-    const int nv = (e.N + SR_THREADS - 1) / SR_THREADS;
-    int s0 = 0;
-    for (; s0 + 4 <= e.splits; s0 += 4) {   // four planes per trip: 4 * nv independent loads in flight
-        const float* ps = p + (size_t)s0 * plane;
-        float t[4][SR_MAXV];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int i = 0; i < SR_MAXV; ++i) {
-                const int n = tid + i * SR_THREADS;
-                t[u][i] = (i < nv && n < e.N) ? __ldcg(ps + (size_t)u * plane + n) : 0.0f;
-            }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int i = 0; i < SR_MAXV; ++i) vals[i] += t[u][i];   // fixed order s0, s0+1, ...: deterministic
-    }
-    for (; s0 < e.splits; ++s0) {
-        const float* ps = p + (size_t)s0 * plane;
-#pragma unroll
-        for (int i = 0; i < SR_MAXV; ++i) {
-            const int n = tid + i * SR_THREADS;
-            if (i < nv && n < e.N) vals[i] += __ldcg(ps + n);
-        }
-    }
     float lsum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < SR_MAXV; ++i) {
-        const int n = tid + i * SR_THREADS;
-        if (i < nv && n < e.N) {
-            float v = vals[i];
-            if (e.bias) v += __ldg(e.bias + n);
-            if (e.act == 1) v = gelu_tanh_fast(v);
-            if (e.x) {
-                v += e.x[(size_t)r * e.N + n];
-                e.x[(size_t)r * e.N + n] = v;
-            }
-            if (e.out) static_cast<T*>(e.out)[(size_t)r * e.out_ld + n] = from_f32<T>(v);
-            if (e.rows && n >= e.d) {
-                const int c = n - e.d, which = c >= e.d, i2 = which ? c - e.d : c;
-                T* panel = static_cast<T*>(which ? e.vpanel : e.kpanel);
-                panel[(size_t)rd.kv_slot * e.slot_stride + ((size_t)(i2 >> 6) * e.n_pos_cap + rd.pos) * 64 + (i2 & 63)] = from_f32<T>(v);
-            }
-            lsum += v;
-            vals[i] = v;
+    for (int g = 0; g < SR_MAXG; ++g) {
+        const int c4 = tid + g * SR_THREADS;
+        vals[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 >= n4) continue;
+        const int n = c4 * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < e.splits; s0 += SR_PLANES) {   // fixed order s0, s0+1, ...: deterministic
+            float4 t[SR_PLANES];
+#pragma unroll
+            for (int u = 0; u < SR_PLANES; ++u)
+                t[u] = (s0 + u < e.splits) ? __ldcg(reinterpret_cast<const float4*>(p + (size_t)(s0 + u) * plane + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < SR_PLANES; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
         }
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (e.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (e.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gelu_tanh_fast(v[i]);
+        }
+        if (e.x) {
+            float4* xp = reinterpret_cast<float4*>(e.x + (size_t)r * e.N + n);
+            const float4 xv = *xp;
+            v[0] += xv.x; v[1] += xv.y; v[2] += xv.z; v[3] += xv.w;
+            *xp = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        if (e.out) {
+            store4<T>(static_cast<T*>(e.out) + (size_t)r * e.out_ld + n, v);
+        }
+        if (e.rows && n >= e.d) {   // 4 consecutive columns never straddle a 64-wide head block
+            const int c = n - e.d, which = c >= e.d, i2 = which ? c - e.d : c;
+            T* dst = static_cast<T*>(which ? e.vpanel : e.kpanel) + (size_t)rd.kv_slot * e.slot_stride + ((size_t)(i2 >> 6) * e.n_pos_cap + rd.pos) * 64 + (i2 & 63);
+            store4<T>(dst, v);
+        }
+        lsum += (v[0] + v[1]) + (v[2] + v[3]);
+        vals[g] = make_float4(v[0], v[1], v[2], v[3]);
     }
     if (e.ln_g) {
         const float mean = block_reduce(lsum, 0.0f, OpAddF(), red) / e.N;
         float lvar = 0.0f;
 #pragma unroll
-        for (int i = 0; i < SR_MAXV; ++i) {
-            const int n = tid + i * SR_THREADS;
-            if (n < e.N) { const float t = vals[i] - mean; lvar += t * t; }
+        for (int g = 0; g < SR_MAXG; ++g) {
+            if (tid + g * SR_THREADS < n4) {
+                const float a = vals[g].x - mean, b = vals[g].y - mean, c = vals[g].z - mean, dd = vals[g].w - mean;
+                lvar += (a * a + b * b) + (c * c + dd * dd);
+            }
         }
         const float var = block_reduce(lvar, 0.0f, OpAddF(), red) / e.N;
         const float inv = rsqrtf(var + 1e-5f);
         T* y = static_cast<T*>(e.y) + (size_t)r * e.N;
 #pragma unroll
-        for (int i = 0; i < SR_MAXV; ++i) {
-            const int n = tid + i * SR_THREADS;
-            if (n < e.N) y[n] = from_f32<T>((vals[i] - mean) * inv * __ldg(e.ln_g + n) + __ldg(e.ln_b + n));
+        for (int g = 0; g < SR_MAXG; ++g) {
+            const int c4 = tid + g * SR_THREADS;
+            if (c4 < n4) {
+                const int n = c4 * 4;
+                const float4 gg = __ldg(reinterpret_cast<const float4*>(e.ln_g + n)), bb = __ldg(reinterpret_cast<const float4*>(e.ln_b + n));
+                const float o[4] = {(vals[g].x - mean) * inv * gg.x + bb.x, (vals[g].y - mean) * inv * gg.y + bb.y,
+                                    (vals[g].z - mean) * inv * gg.z + bb.z, (vals[g].w - mean) * inv * gg.w + bb.w};
+                store4<T>(y + n, o);
+            }
         }
     }
 }

@@ -104,3 +104,34 @@ def test_encoder_attention_kernel(n_win, n_head, use_simt):
             got = out[w * 1536:(w + 1) * 1536, h * 64:(h + 1) * 64]
             assert np.abs(got[:1500] - ref[:1500]).max() < 2e-2 * max(1.0, np.abs(ref).max())
             assert np.isfinite(got).all()
+
+
+@pytest.mark.parametrize("R,n_head,n_slots,n_keys,streaming", [(3, 2, 2, 1500, 2), (5, 20, 3, 1500, 2), (130, 6, 4, 1500, 2), (2, 1, 1, 77, 2),
+                                                                (4, 3, 2, 1280, 2), (3, 2, 2, 1500, 1), (130, 6, 4, 1500, 1), (2, 1, 1, 77, 1),
+                                                                (3, 2, 2, 1500, 0)])
+def test_decoder_cross_attention_kernel(R, n_head, n_slots, n_keys, streaming):
+    """Streaming cross-attention kernels (2: tcgen05, 1: SIMT over a cp.async.bulk ring, 0: block-per-head SIMT)
+    against a float64 softmax(q K^T / 8) V over head-major panels; more items than SMs, ragged last chunk,
+    rows sharing a slot.  Pad rows past n_keys hold large finite garbage that must not reach the result."""
+    from nobs_whisper_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(R * 100 + n_head)
+    d = 64 * n_head
+    q = (1.5 * rng.standard_normal((R, d))).astype(np.float32)
+    k = rng.standard_normal((n_slots, n_head, 1536, 64)).astype(np.float32)
+    v = rng.standard_normal((n_slots, n_head, 1536, 64)).astype(np.float32)
+    k[:, :, n_keys:] = 1e4      # rows past n_keys must never reach the result
+    v[:, :, n_keys:] = -3e3
+    out = np.zeros((R, d), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    rc = L.whisper_b200_debug_dec_cross_attention(R, n_head, n_slots, n_keys, fp(q), fp(k), fp(v), fp(out), streaming)
+    assert rc == 0, (rc, L.whisper_b200_last_error())
+    assert np.isfinite(out).all()
+    qb, kb, vb = to_bf16(q).astype(np.float64), to_bf16(k[:, :, :n_keys]).astype(np.float64), to_bf16(v[:, :, :n_keys]).astype(np.float64)
+    for r in range(R):
+        s_ = r % n_slots
+        for h in range(n_head):
+            sc = kb[s_, h] @ qb[r, h * 64:(h + 1) * 64] * 0.125
+            p = np.exp(sc - sc.max())
+            ref = (p / p.sum()) @ vb[s_, h]
+            assert np.abs(out[r, h * 64:(h + 1) * 64] - ref).max() < (2e-2 if streaming == 2 else 1e-2) * max(1.0, np.abs(ref).max())
