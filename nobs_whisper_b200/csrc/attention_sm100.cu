@@ -255,6 +255,7 @@ bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int 
         configured = true;
     }
     dim3 grid(kWinRows / AQ, n_head, n_win);
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&enc_attention_sm100_kernel));
     enc_attention_sm100_kernel<<<grid, 192, ATT_SMEM, s>>>(tm, out, d, 1500);
     count_launch();
     const cudaError_t err = cudaGetLastError();

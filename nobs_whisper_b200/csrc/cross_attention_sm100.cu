@@ -279,6 +279,7 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
     int* item_q = reinterpret_cast<int*>(red + 8);          // [QD]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tr = trace_begin(4, out);
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_kv);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -378,6 +379,7 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
         };
         if (threadIdx.x == 0) { fetch(0); fetch(1); }   // the counter does not depend on the predecessor kernel
         pdl_wait();   // q does
+        trace_end(trace_begin(104, out));
         auto put_q = [&](int item, int buf) {   // 128 bytes of q -> row 0 of the q tile (row 0 of a swizzle atom is stored linearly)
             if (warp == 0) {
                 if (lane < 8) {
@@ -472,6 +474,7 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
         tc_fence_after();
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
     }
+    trace_end(tr);
     // the last CTA to leave re-arms the counters for the next launch on this lane
     if (threadIdx.x == 0) {
         __threadfence();
@@ -484,6 +487,11 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
 }
 
 }  // namespace
+
+void trace_set_cross(unsigned long long* buf, unsigned int cap) {
+    cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+}
 
 namespace {
 int env_or(const char* name, int dflt);
@@ -518,9 +526,9 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
-        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 8);
-        sp = env_or("NOBS_WHISPER_CROSS_SPACING", 16);
-        per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 1);
+        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 4);
+        sp = env_or("NOBS_WHISPER_CROSS_SPACING", 4);
+        per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 2);
     }
     // one tensor map over the whole pool viewed as [rows][64] (re-encoded when the pool moves or grows)
     thread_local const bf16* cached_pool = nullptr;
@@ -579,9 +587,9 @@ bool launch_dec_cross_attention_sm100(const RowDesc* rows, int n_rows, const bf1
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
-        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 6);
-        warps = env_or("NOBS_WHISPER_CROSS_WARPS", 8);
-        per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 1);
+        stages = env_or("NOBS_WHISPER_CROSS_SIMT_STAGES", 3);
+        warps = env_or("NOBS_WHISPER_CROSS_SIMT_WARPS", 8);
+        per_sm = env_or("NOBS_WHISPER_CROSS_SIMT_PER_SM", 2);
     }
     const int n_items = n_rows * n_head;
     int grid = n_items < sms * per_sm ? n_items : sms * per_sm;

@@ -11,6 +11,32 @@ namespace nobs {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Kernel timeline (debugging aid, NOBS_WHISPER_TRACE): block (0,0) thread 0 of an instrumented kernel appends
+// {kernel id, tag, start ns, end ns} (globaltimer) to a device buffer whose first word is the entry counter.
+// One pointer per translation unit (no relocatable device code), all set to the same buffer by trace_set_*().
+static __device__ unsigned long long* g_trace = nullptr;
+static __device__ unsigned int g_trace_cap = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ long long trace_begin(int kid, const void* tag) {
+    unsigned long long* buf = g_trace;
+    if (!buf || (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) != 0) return -1;
+    const unsigned long long i = atomicAdd(buf, 1ull);
+    if (i >= g_trace_cap) return -1;
+    unsigned long long* e = buf + 4 + 4 * i;
+    e[0] = (unsigned long long)kid;
+    e[1] = (unsigned long long)tag;
+    e[2] = globaltimer_ns();
+    e[3] = 0;
+    return (long long)i;
+}
+__device__ __forceinline__ void trace_end(long long i) {
+    if (i >= 0) g_trace[4 + 4 * i + 3] = globaltimer_ns();
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

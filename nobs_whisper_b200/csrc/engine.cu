@@ -90,6 +90,20 @@ public:
             for (int i = 0; i < 8; ++i)
                 if (detail_n_[i]) fprintf(stderr, "[nobs profile] %-14s n=%8ld total=%10.2f ms avg=%8.2f us\n", names[i], detail_n_[i], detail_ms_[i], 1e3 * detail_ms_[i] / detail_n_[i]);
         }
+        if (trace_buf_) {
+            cudaDeviceSynchronize();
+            unsigned long long n = 0;
+            cudaMemcpy(&n, trace_buf_, 8, cudaMemcpyDeviceToHost);
+            n = std::min<unsigned long long>(n, trace_cap_);
+            const unsigned long long skip = std::min<unsigned long long>(n, (unsigned long long)std::max(0, env_int("NOBS_WHISPER_TRACE_SKIP", 0)));
+            const unsigned long long cnt = std::min<unsigned long long>(n - skip, (unsigned long long)std::max(1, env_int("NOBS_WHISPER_TRACE_COUNT", 400000)));
+            std::vector<unsigned long long> h(4 * cnt);
+            cudaMemcpy(h.data(), trace_buf_ + 4 + 4 * skip, h.size() * 8, cudaMemcpyDeviceToHost);
+            if (FILE* f = fopen(trace_path_.c_str(), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+            fprintf(stderr, "[nobs trace] %llu entries recorded, wrote %llu from %llu to %s\n", n, cnt, skip, trace_path_.c_str());
+            trace_set_kernels(nullptr, 0); trace_set_gemm(nullptr, 0); trace_set_cross(nullptr, 0);
+            cudaFree(trace_buf_);
+        }
         for (auto& e : main_marks_.pool) cudaEventDestroy(e);
         for (auto& L : lanes_) {
             if (L.stream) cudaStreamSynchronize(L.stream);
@@ -119,6 +133,15 @@ public:
                              v.token_nosp, v.token_not, v.token_beg, v.token_blank, kNumLangs};
         if (!upload_weights(hm)) return false;
         if (!alloc_workspace()) return false;
+        if (const char* tp = getenv("NOBS_WHISPER_TRACE")) {   // kernel timeline (debugging aid)
+            trace_path_ = tp;
+            trace_cap_ = (unsigned)std::max(1024, env_int("NOBS_WHISPER_TRACE_CAP", 3000000));
+            CUDA_OK(cudaMalloc(&trace_buf_, (4 + 4 * (size_t)trace_cap_) * 8));
+            CUDA_OK(cudaMemset(trace_buf_, 0, (4 + 4 * (size_t)trace_cap_) * 8));
+            trace_set_kernels(trace_buf_, trace_cap_);
+            trace_set_gemm(trace_buf_, trace_cap_);
+            trace_set_cross(trace_buf_, trace_cap_);
+        }
         CUDA_OK(cudaStreamSynchronize(stream_));
         return true;
     }
@@ -1050,6 +1073,9 @@ private:
     static constexpr int kCrossSample = 8;  // profiling: time the cross-attention of every 8th layer
 
     cudaEvent_t user_ev_[8] = {};
+    unsigned long long* trace_buf_ = nullptr;
+    unsigned trace_cap_ = 0;
+    std::string trace_path_;
     char* pin_ = nullptr;
     size_t pin_cap_ = 0;
     char* dev_scratch_ = nullptr;

@@ -82,6 +82,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tr = trace_begin(5, C);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
@@ -92,12 +93,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
-    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();   // the successor's prologue overlaps this kernel's work (never more than one kernel parked ahead)
 
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
@@ -208,6 +209,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tc_fence_after();
         tmem_dealloc(tmem_base, cfg::TMEM_COLS);
     }
+    trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -240,6 +242,7 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, split = blockIdx.y;
+    const long long tr = trace_begin(1, partial);
     const int num_k = (K + BK - 1) / BK;
     const int kb0 = split * kb_per_split, kb1 = min(num_k, kb0 + kb_per_split);
 
@@ -253,7 +256,6 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
-    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -270,6 +272,8 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
             }
         }
         pdl_wait();
+        pdl_launch_dependents();   // successor prologue overlaps this kernel's work; never more than one kernel parked ahead
+        trace_end(trace_begin(101, partial));
         if (lane == 0) {
             for (int i = 0; i < pre; ++i) tma_load_2d(sB + i * B_BYTES, &tmap_x, &full[i], (kb0 + i) * BK, 0);
         }
@@ -328,6 +332,7 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -347,6 +352,11 @@ EncodeTiledFn encode_fn() {
 }
 
 }  // namespace
+
+void trace_set_gemm(unsigned long long* buf, unsigned int cap) {
+    cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+}
 
 void sm100_set_error(const std::string& e) { g_err = e; }
 

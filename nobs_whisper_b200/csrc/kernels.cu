@@ -9,6 +9,8 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_set>
 
 namespace nobs {
 
@@ -16,6 +18,20 @@ bool g_use_pdl = [] { const char* e = getenv("NOBS_WHISPER_PDL"); return !(e && 
 static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void trace_set_kernels(unsigned long long* buf, unsigned int cap) {
+    cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+}
+
+void prefer_max_shared_carveout(const void* kernel) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> seen;
+    static const bool enabled = [] { const char* v = getenv("NOBS_WHISPER_MAX_CARVEOUT"); return v && *v == '1'; }();  // measured: no effect on lane overlap, costs the encoder ~6 %
+    if (!enabled) return;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 #define NOBS_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 // ------------------------------------------------------------------------------------------
@@ -127,6 +143,7 @@ void launch_mel_stft(const MelTables& t, const MelJob* jobs_dev, int n_jobs, int
     if (n_jobs <= 0 || max_frames <= 0) return;
     const int frames_per_block = 32;
     dim3 grid((max_frames + frames_per_block - 1) / frames_per_block, n_jobs);
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&mel_stft_kernel));
     mel_stft_kernel<<<grid, kMelWarps * 32, 0, s>>>(t, jobs_dev, frames_per_block);
     NOBS_COUNT_LAUNCH();
 }
@@ -164,6 +181,7 @@ template <typename T>
 void launch_pack_mel(const PackJob* jobs_dev, int n_win, int n_mel, T* dst, cudaStream_t s) {
     if (n_win <= 0) return;
     dim3 grid((kWinRowsIn * n_mel + 255) / 256, n_win);
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&pack_mel_kernel<T>));
     pack_mel_kernel<T><<<grid, 256, 0, s>>>(jobs_dev, n_mel, dst);
     NOBS_COUNT_LAUNCH();
 }
@@ -265,8 +283,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ idx,
                                                         const float* __restrict__ g, const float* __restrict__ b, TO* __restrict__ y,
                                                         int ldy, int rows, int d) {
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -473,6 +491,7 @@ __global__ void embed_kernel(const RowDesc* __restrict__ rows, int n_rows, const
 template <typename T>
 void launch_embed(const RowDesc* rows, int n_rows, const T* tok_emb, const float* pos_emb, float* x, int d, cudaStream_t s) {
     if (n_rows <= 0) return;
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&embed_kernel<T>));
     embed_kernel<T><<<n_rows, 128, 0, s>>>(rows, n_rows, tok_emb, pos_emb, x, d);
     NOBS_COUNT_LAUNCH();
 }
@@ -496,6 +515,7 @@ template <typename T>
 void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kpanel0, T* vpanel0, size_t slot_stride, int n_pos_cap, int d,
                        cudaStream_t s) {
     if (n_rows <= 0) return;
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&scatter_kv_kernel<T>));
     scatter_kv_kernel<T><<<n_rows, 128, 0, s>>>(rows, qkv, kpanel0, vpanel0, slot_stride, n_pos_cap, d);
     NOBS_COUNT_LAUNCH();
 }
@@ -552,8 +572,8 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
     __shared__ float sc[kWinRows];
     __shared__ float red[32];
     __shared__ float part[KPI][64 + 1];
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
     const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const RowDesc rd = rows[r];
     const int nk = cross ? n_keys : rd.pos + 1;
@@ -634,45 +654,44 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
         out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o * inv);
     }
 }
-// Causal self-attention over the (short) self-KV panel: one warp per (row, head), no block barriers.
-// At most 448 keys: the block-per-head kernel above is latency-bound there (4 resident blocks per SM
-// each paying several barrier round trips); a warp streams its <= 56 KB panel with shuffles only.
+// Causal self-attention over the (short) self-KV panel: one 4-warp block per (row, head), the keys interleaved
+// over the warps (16-byte lanes as above), so the longest sequence of a step batch costs a quarter of a
+// warp-per-head pass: this kernel sits on the latency chain of every decoder layer.
+constexpr int SA_WARPS = 4;
 template <typename T>
-__global__ void __launch_bounds__(128) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
-                                                                 const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out, int ldo,
-                                                                 int n_head, size_t slot_stride, size_t head_stride) {
-    constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, UNR = 8;
-    __shared__ float sc[4][448];
-    __shared__ float qs[4][64];
-    pdl_launch_dependents();
+__global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+                                                                          const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out,
+                                                                          int ldo, int n_head, size_t slot_stride, size_t head_stride) {
+    constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 4;
+    __shared__ float sc[448];
+    __shared__ float red[2 * SA_WARPS];
+    __shared__ float part[SA_WARPS][64];
+    const long long tr = trace_begin(3, out);
     pdl_wait();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x, h = blockIdx.y * 4 + warp;
-    if (h >= n_head) return;
+    pdl_launch_dependents();
+    trace_end(trace_begin(103, out));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int r = blockIdx.x, h = blockIdx.y;
     const RowDesc rd = rows[r];
     const int nk = min(rd.pos + 1, 448);
     const size_t base = (size_t)rd.kv_slot * slot_stride + (size_t)h * head_stride;
     const T* K = kc + base;
     const T* V = vc + base;
-    qs[warp][lane] = to_f32(q[(size_t)r * ldq + h * 64 + lane]);
-    qs[warp][lane + 32] = to_f32(q[(size_t)r * ldq + h * 64 + lane + 32]);
-    __syncwarp();
-    const int sub = lane % LPK, ks = lane / LPK;
+    const int sub = lane % LPK, ks = warp * KPW + lane / LPK;   // key slot of this thread within a block iteration
     float qv[VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) qv[i] = qs[warp][sub * VN + i];
-    float* s_w = sc[warp];
+    for (int i = 0; i < VN; ++i) qv[i] = to_f32(q[(size_t)r * ldq + h * 64 + sub * VN + i]);
     float lmax = -INFINITY;
-    for (int j0 = 0; j0 < nk; j0 += UNR * KPW) {
+    for (int j0 = 0; j0 < nk; j0 += UNR * KPB) {
         typename Vec16<T>::Raw raw[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int j = j0 + u * KPW + ks;
+            const int j = j0 + u * KPB + ks;
             raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int j = j0 + u * KPW + ks;
+            const int j = j0 + u * KPB + ks;
             float kvv[VN];
             Vec16<T>::unpack(raw[u], kvv);
             float acc = 0.0f;
@@ -682,35 +701,44 @@ __global__ void __launch_bounds__(128) dec_self_attention_kernel(const RowDesc* 
             for (int o = LPK / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (j < nk) {
                 acc *= 0.125f;
-                if (sub == 0) s_w[j] = acc;
+                if (sub == 0) sc[j] = acc;
                 lmax = fmaxf(lmax, acc);
             }
         }
     }
-    const float mx = warp_max(lmax);
-    __syncwarp();
+    lmax = warp_max(lmax);
+    if (lane == 0) red[warp] = lmax;
+    __syncthreads();
+    float mx = red[0];
+#pragma unroll
+    for (int w = 1; w < SA_WARPS; ++w) mx = fmaxf(mx, red[w]);
     float lsum = 0.0f;
-    for (int j = lane; j < nk; j += 32) {
-        const float p = expf(s_w[j] - mx);
-        s_w[j] = p;
+    for (int j = tid; j < nk; j += SA_WARPS * 32) {
+        const float p = expf(sc[j] - mx);
+        sc[j] = p;
         lsum += p;
     }
-    const float inv = 1.0f / warp_sum(lsum);
-    __syncwarp();
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[SA_WARPS + warp] = lsum;
+    __syncthreads();
+    float total = 0.0f;
+#pragma unroll
+    for (int w = 0; w < SA_WARPS; ++w) total += red[SA_WARPS + w];
+    const float inv = 1.0f / total;
     float acc[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
-    for (int j0 = 0; j0 < nk; j0 += UNR * KPW) {
+    for (int j0 = 0; j0 < nk; j0 += UNR * KPB) {
         typename Vec16<T>::Raw raw[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int j = j0 + u * KPW + ks;
+            const int j = j0 + u * KPB + ks;
             raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int j = j0 + u * KPW + ks;
-            const float p = j < nk ? s_w[j] : 0.0f;
+            const int j = j0 + u * KPB + ks;
+            const float p = j < nk ? sc[j] : 0.0f;
             float vvv[VN];
             Vec16<T>::unpack(raw[u], vvv);
 #pragma unroll
@@ -722,11 +750,18 @@ __global__ void __launch_bounds__(128) dec_self_attention_kernel(const RowDesc* 
 #pragma unroll
         for (int o = 16; o >= LPK; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
-    if (ks == 0) {
-        T* dst = out + (size_t)r * ldo + h * 64 + sub * VN;
+    if (lane < LPK) {
 #pragma unroll
-        for (int i = 0; i < VN; ++i) dst[i] = from_f32<T>(acc[i] * inv);
+        for (int i = 0; i < VN; ++i) part[warp][sub * VN + i] = acc[i];
     }
+    __syncthreads();
+    if (tid < 64) {
+        float o = 0.0f;
+#pragma unroll
+        for (int w = 0; w < SA_WARPS; ++w) o += part[w][tid];   // fixed order
+        out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o * inv);
+    }
+    trace_end(tr);
 }
 
 template <typename T>
@@ -734,8 +769,8 @@ void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, 
                           int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s) {
     if (n_rows <= 0) return;
     if (!cross) {
-        dim3 grid(n_rows, (n_head + 3) / 4);
-        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(128), 0, s, true, rows, q, ldq, kbase, vbase, out, ldo, n_head, slot_stride, head_stride);
+        dim3 grid(n_rows, n_head);
+        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, kbase, vbase, out, ldo, n_head, slot_stride, head_stride);
         NOBS_COUNT_LAUNCH();
         return;
     }
@@ -761,6 +796,7 @@ template <typename T>
 void launch_kv_copy(const KvCopy* pairs, int n_pairs, T* pool, size_t slot_stride, int n_panels, size_t panel_stride, cudaStream_t s) {
     if (n_pairs <= 0) return;
     dim3 grid(n_pairs, n_panels);
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&kv_copy_kernel<T>));
     kv_copy_kernel<T><<<grid, 128, 0, s>>>(pairs, pool, slot_stride, panel_stride);
     NOBS_COUNT_LAUNCH();
 }
@@ -789,8 +825,10 @@ constexpr int SR_PLANES = 8; // split-K planes summed per trip (independent 16-b
 template <typename T>
 __global__ void __launch_bounds__(SR_THREADS, 4) skinny_reduce_kernel(SkinnyEpilogue e) {
     __shared__ float red[32];
-    pdl_launch_dependents();
+    const long long tr = trace_begin(2, e.partial);
     pdl_wait();
+    pdl_launch_dependents();   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
+    trace_end(trace_begin(102, e.partial));
     const int r = blockIdx.x, tid = threadIdx.x;
     const size_t plane = (size_t)e.R * e.N;
     const float* p = e.partial + (size_t)r * e.N;
@@ -865,6 +903,7 @@ __global__ void __launch_bounds__(SR_THREADS, 4) skinny_reduce_kernel(SkinnyEpil
             }
         }
     }
+    trace_end(tr);
 }
 template <typename T>
 void launch_skinny_reduce(const SkinnyEpilogue& e, cudaStream_t s) {
@@ -906,8 +945,8 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
     __shared__ int s_pick;
     __shared__ int s_chosen[kMaxTopK];
 
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
     const int row = blockIdx.x, tid = threadIdx.x;
     const SampleParams p = params[row];
     const float* lg = logits + (size_t)row * ld;
@@ -1088,6 +1127,7 @@ __global__ void lang_probs_kernel(const float* __restrict__ logits, VocabIds v, 
     if (tid == 0) *best = b;
 }
 void launch_lang_probs(const float* logits, const VocabIds& v, float* probs_out, int* best, cudaStream_t s) {
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(&lang_probs_kernel));
     lang_probs_kernel<<<1, 128, 0, s>>>(logits, v, probs_out, best);
     NOBS_COUNT_LAUNCH();
 }

@@ -169,6 +169,9 @@ void launch_convert_2d(const TI* in, size_t ld_in, TO* out, size_t ld_out, int r
 
 // Launch with (or without) the programmatic-dependent-launch attribute.
 extern bool g_use_pdl;
+// Opt-in (NOBS_WHISPER_MAX_CARVEOUT=1): ask for the maximum shared-memory carveout for every kernel, so that SMs
+// never have to drain to change their L1 / shared-memory split when kernels of different decode lanes share them.
+void prefer_max_shared_carveout(const void* kernel);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -181,9 +184,14 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+    prefer_max_shared_carveout(reinterpret_cast<const void*>(kernel));
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// kernel timeline buffer (device_utils.cuh); one setter per translation unit
+void trace_set_kernels(unsigned long long* buf, unsigned int cap);
+void trace_set_gemm(unsigned long long* buf, unsigned int cap);
+void trace_set_cross(unsigned long long* buf, unsigned int cap);
 long kernel_launch_count();  // process-wide count of kernels launched through these launchers
 void count_launch();
 
