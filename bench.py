@@ -16,8 +16,13 @@ and a max-reduce of the times), `value` = all ranks' audio-seconds / max-over-ra
            (barrier + cuda synchronize both sides)
   e2e    : the same through the public host API (WhisperEngine.transcribe_batch over pinned
            host PCM): H2D of the PCM and D2H of the transcripts are inside the timed region.
-  roofline: the dominant kernel (bf16 tcgen05 GEMM, encoder side): algorithmic FLOPs / summed
-           per-launch CUDA-event durations recorded inside the timed steps.
+  roofline: the dominant kernel (decoder cross-attention stream over the cross-KV panels, HBM-bound):
+           algorithmic K/V bytes / summed per-launch CUDA-event durations recorded inside the timed
+           steps (on the decode lane's own stream).  Two decode lanes share the GPU, so a launch is
+           timed while the other lane's projection kernels run beside it; `isolated` is the same
+           kernel timed alone in this process.  Encoder GEMM / attention are listed as other_kernels.
+  latency : BASELINE.json's second metric — p50 / p99 end-to-end latency of one 5-s utterance on
+           large-v3-turbo through WhisperEngine.transcribe (host PCM in, text out), wall clock.
   cpu_baseline: the oracle (CPU restatement of the reference path) on a bounded sample.
 
 `--impl reference` times the reference's own CPU path.  whisper-rs / whisper.cpp are not
@@ -126,6 +131,27 @@ def make_audio(n_windows: int, first: int):
     return [synth_audio.synth_clip(first + i, WINDOW_S) for i in range(n_windows)]
 
 
+def turbo_latency(n_clips: int):
+    """BASELINE.json configs[4]: large-v3-turbo, hotkey-style 5-s utterances, one at a time through the
+    reference-facing call (WhisperEngine.transcribe: host PCM in, text out); wall clock per utterance."""
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import ggml_synth, synth_audio
+    path = ggml_synth.ensure_model(MODEL_DIR, "large-v3-turbo", seed=0, ftype=1, init="survey")
+    eng = nw.WhisperEngine()
+    eng.load_model(path)
+    clips = [synth_audio.synth_clip(5000 + i, 5.0) for i in range(n_clips + 3)]
+    ms = []
+    for i, c in enumerate(clips):
+        t0 = time.perf_counter()
+        eng.transcribe(c, "en", None, None)
+        if i >= 3:   # three warm-up utterances
+            ms.append(1e3 * (time.perf_counter() - t0))
+    eng.close()
+    return {"workload": "whisper large-v3-turbo (32 + 4 layers) bf16, 5-s synthetic utterances, greedy + temperature fallback, one utterance per call",
+            "n": len(ms), "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)), "mean_ms": float(np.mean(ms)),
+            "timing": "host wall clock around WhisperEngine.transcribe (H2D of the PCM and D2H of the text included)"}
+
+
 def run_reference(args, rank, world, arch_name):
     """--impl reference: the oracle port on the host cores, bounded sample per step."""
     if rank != 0:
@@ -173,6 +199,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-windows", type=int, default=1, help="bounded sample for the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-clips", type=int, default=24, help="5-s utterances for the large-v3-turbo latency figure (0: skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -291,12 +318,13 @@ def main():
         cross_s = agg_dev["cross_ms"] / 1e3
         cross_gbs = agg_dev["cross_bytes"] / cross_s / 1e9 if cross_s > 0 else 0.0
         roofline = {
-            "bound": "hbm", "kernel": "dec_attention_kernel<bf16> (decoder cross-attention over the head-major cross-KV panels)",
+            "bound": "hbm", "kernel": "dec_cross_attention_tc_kernel (decoder cross-attention: TMA ring -> tcgen05 over the head-major cross-KV panels)",
             "achieved": cross_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cross_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
             "traffic": None, "peak_source": peaks["source"] + " hbm_gbs", "launches": agg_dev["cross_n"],
             "algorithmic_bytes_per_launch": agg_dev["cross_bytes"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
             "avg_launch_us": 1e3 * agg_dev["cross_ms"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
-            "share_of_step": agg_dev["cross_ms"] / (1000.0 * dt_dev) if dt_dev else None,
+            # every 8th layer's launch is timed (engine.cu kCrossSample): extrapolated share of the decode lanes' stream time
+            "launches_timed_of": 8, "share_of_decode_lane_time": 8.0 * agg_dev["cross_ms"] / agg_dev["ms_dec"] if agg_dev["ms_dec"] else None,
             "other_kernels": {
                 "gemm_bf16_sm100_kernel (encoder side: conv stem, QKV/out/MLP, cross-KV projection)": {
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
@@ -306,6 +334,22 @@ def main():
                     "launches": agg_dev["attn_n"], "share_of_step": agg_dev["attn_ms"] / (1000.0 * dt_dev) if dt_dev else None},
             },
         }
+        # the same kernel alone on the GPU (micro-benchmark hook of the library, rows of one lane)
+        try:
+            import ctypes as C
+            from nobs_whisper_b200 import _lib
+            us = np.zeros(16, np.float32)
+            r_iso = max(1, min(128, int(round(agg_dev["rows"] / max(agg_dev["rounds"], 1) / max(eng.n_lanes(), 1)))))
+            if _lib.lib().whisper_b200_debug_time_decode_kernels(r_iso, arch.n_text_state, 50, us.ctypes.data_as(C.POINTER(C.c_float))) == 0 and us[12] > 0:
+                iso_bytes = 2.0 * r_iso * 1500 * arch.n_text_state * 2
+                iso_us = float(us[12])
+                roofline["isolated"] = {"rows": int(r_iso), "avg_launch_us": iso_us, "achieved": float(iso_bytes / (iso_us * 1e-6) / 1e9),
+                                        "frac": float(iso_bytes / (iso_us * 1e-6) / 1e9 / peaks["hbm_gbs"])}
+        except Exception as exc:  # the figure is auxiliary
+            roofline["isolated"] = {"error": str(exc)}
+        latency = None
+        if args.latency_clips > 0 and world == 1:
+            latency = turbo_latency(args.latency_clips)
         line = {
             "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -316,7 +360,8 @@ def main():
                 "windows_per_gpu": n_win, "weights": "random-init N(0,0.02) ggml f16 file, seed 0", "l2": "inputs and weights exceed L2 (3.1 GB weights, 30 GB cross-KV)",
                 "decoder_rows_per_step": agg_dev["rows"] / steps, "sampled_tokens_per_step": agg_dev["samples"] / steps,
                 "decoder_rounds_per_step": agg_dev["rounds"] / steps, "fallbacks_per_step": agg_dev["fallbacks"] / steps,
-                "stage_ms_per_step": {"mel": agg_dev["ms_mel"] / steps, "encode": agg_dev["ms_enc"] / steps, "decode": agg_dev["ms_dec"] / steps},
+                "stage_ms_per_step": {"mel": agg_dev["ms_mel"] / steps, "encode": agg_dev["ms_enc"] / steps,
+                                      "decode_lane_sum": agg_dev["ms_dec"] / steps, "decode_lanes": eng.n_lanes()},
                 "x_realtime": value, "timing": "CUDA events on the library stream around the K steps, max over ranks",
                 "host_wall_ms_per_step": 1000.0 * agg_dev["wall_s"] / steps,
             },
@@ -326,8 +371,9 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
+            "latency": latency,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=float), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -179,6 +179,7 @@ SIGNATURES = {
     "whisper_lang_auto_detect_with_state": (C.c_int, [vp, vp, C.c_int, C.c_int, fp]),
     "whisper_b200_init_from_file": (vp, [C.c_char_p, WhisperContextParams, C.c_int]),
     "whisper_b200_precision": (C.c_int, [vp]),
+    "whisper_b200_decode_lanes": (C.c_int, [vp]),
     "whisper_b200_init_host_only": (vp, [C.c_char_p]),
     "whisper_b200_full_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, WhisperFullParams, C.POINTER(fp), ip, ip]),
     "whisper_b200_get_mel": (C.c_int, [vp, fp, C.c_size_t]),

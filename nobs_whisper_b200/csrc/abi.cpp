@@ -92,6 +92,8 @@ int whisper_b200_precision(struct whisper_context* ctx) {
     return ctx && ctx->engine ? (int)ctx->engine->precision() : 0;
 }
 
+int whisper_b200_decode_lanes(struct whisper_context* ctx) { return ctx && ctx->engine ? ctx->engine->n_lanes() : 0; }
+
 struct whisper_state* whisper_init_state(struct whisper_context* ctx) {
     if (!ctx || !ctx->engine) { set_last_error("null context"); return nullptr; }
     auto* st = new whisper_state();

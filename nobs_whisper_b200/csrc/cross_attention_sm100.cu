@@ -544,7 +544,7 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     bool ok = false;
 #define TC_CASE(S, P) if (stages == S && sp == P) ok = launch_tc<S, P>(tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, grid, s); else
-    TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
+    TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(2, 4) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
     { sm100_set_error("cross attention (tc): unsupported NOBS_WHISPER_CROSS_STAGES / _SPACING"); return false; }
 #undef TC_CASE
     if (!ok) return false;

@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
 // Causal self-attention over the (short) self-KV panel: one 4-warp block per (row, head), the keys interleaved
 // over the warps (16-byte lanes as above), so the longest sequence of a step batch costs a quarter of a
 // warp-per-head pass: this kernel sits on the latency chain of every decoder layer.
-constexpr int SA_WARPS = 4;
+constexpr int SA_WARPS = 2;   // R x heads blocks of 64 threads stay one wave at R = 128 (4 warps: 2400 x 128 threads spill into a second wave)
 template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
                                                                           const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out,

@@ -100,6 +100,11 @@ class WhisperEngine:
         self._L.nobs_engine_last_stats(self._h, C.byref(s))
         return s
 
+    def n_lanes(self) -> int:
+        """Decode lanes of the loaded context (0 without a model)."""
+        ctx = self._L.nobs_engine_context(self._h)
+        return int(self._L.whisper_b200_decode_lanes(ctx)) if ctx else 0
+
     def set_profiling(self, on: bool) -> None:
         ctx = self._L.nobs_engine_context(self._h)
         if ctx:
