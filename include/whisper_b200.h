@@ -363,6 +363,22 @@ int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n
  * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..12]; out_us holds 16 floats). */
 int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us);
 
+/* ---- silence chunker (reference src-tauri/src/audio.rs) ----------------------------------
+ * Cuts a long 16 kHz recording into the pieces the transcription path consumes (reference state.rs:757-780).
+ * The per-window RMS runs on the current CUDA device (audio may be host or device memory); the results are
+ * bit-identical to the reference's float32 arithmetic.  Return 0 on success, -1 bad arguments, -100 CUDA failure. */
+/* audio.rs:364-370 for every full window [i*window, (i+1)*window): rms_out receives min(cap, *n_windows) values */
+int whisper_b200_window_rms(const float* audio, size_t n_samples, uint32_t window, float* rms_out, size_t cap, size_t* n_windows);
+/* audio.rs:400-463 find_silence_boundaries(audio, sample_rate): split points (sample indices, centre of each
+ * silence gap >= 700 ms that leaves a chunk >= 1 s), adaptive threshold from the first 25 windows */
+int nobs_find_silence_boundaries(const float* audio, size_t n_samples, uint32_t sample_rate, size_t* boundaries, size_t cap, size_t* n_found);
+/* audio.rs:473-507 split_at_silences_with_overlap: chunk k = audio[ranges[2k], ranges[2k+1]) with 200 ms of the
+ * previous chunk prepended; ranges must hold 2 * (n_boundaries + 1) entries */
+int nobs_split_at_silences_with_overlap(size_t n_samples, const size_t* boundaries, size_t n_boundaries, uint32_t sample_rate, size_t* ranges,
+                                        size_t* n_chunks);
+/* audio.rs:467-469 split_at_silences (16 kHz) */
+int nobs_split_at_silences(size_t n_samples, const size_t* boundaries, size_t n_boundaries, size_t* ranges, size_t* n_chunks);
+
 /* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */
 int whisper_b200_event_record(struct whisper_context* ctx, int slot);
 double whisper_b200_event_elapsed_ms(struct whisper_context* ctx, int slot_a, int slot_b);

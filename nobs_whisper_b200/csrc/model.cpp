@@ -85,6 +85,51 @@ const HostTensor& HostModel::get(const std::string& name) const {
     return it->second;
 }
 
+// ggml block quantisation (32 weights per block), as written by whisper.cpp's `quantize` tool.  Type ids are ggml's:
+// 2 Q4_0 {f16 d; u8 qs[16]}, 3 Q4_1 {f16 d, m; qs[16]}, 6 Q5_0 {f16 d; u8 qh[4]; qs[16]}, 7 Q5_1 {f16 d, m; qh[4]; qs[16]},
+// 8 Q8_0 {f16 d; i8 qs[32]}.  Element j of the low nibbles is weight j, of the high nibbles weight j + 16; the fifth bit of
+// weight i is bit i of qh.
+static int quant_block_bytes(int ttype) {
+    switch (ttype) {
+        case 2: return 18;
+        case 3: return 20;
+        case 6: return 22;
+        case 7: return 24;
+        case 8: return 34;
+        default: return 0;
+    }
+}
+static void dequantize_blocks(int ttype, const uint8_t* src, size_t n_blocks, float* dst) {
+    const int bs = quant_block_bytes(ttype);
+    for (size_t b = 0; b < n_blocks; ++b, src += bs, dst += 32) {
+        uint16_t hd, hm = 0;
+        memcpy(&hd, src, 2);
+        const float d = half_to_float(hd);
+        const uint8_t* q = src + 2;
+        float m = 0.0f;
+        if (ttype == 3 || ttype == 7) { memcpy(&hm, src + 2, 2); m = half_to_float(hm); q += 2; }
+        if (ttype == 8) {
+            for (int j = 0; j < 32; ++j) dst[j] = (float)(int8_t)q[j] * d;
+            continue;
+        }
+        uint32_t qh = 0;
+        if (ttype == 6 || ttype == 7) { memcpy(&qh, q, 4); q += 4; }
+        for (int j = 0; j < 16; ++j) {
+            int x0 = q[j] & 0x0F, x1 = q[j] >> 4;
+            if (ttype == 6 || ttype == 7) {
+                x0 |= (int)(((qh >> j) << 4) & 0x10);
+                x1 |= (int)((qh >> (j + 12)) & 0x10);
+            }
+            switch (ttype) {
+                case 2: dst[j] = (float)(x0 - 8) * d; dst[j + 16] = (float)(x1 - 8) * d; break;
+                case 3: dst[j] = (float)x0 * d + m; dst[j + 16] = (float)x1 * d + m; break;
+                case 6: dst[j] = (float)(x0 - 16) * d; dst[j + 16] = (float)(x1 - 16) * d; break;
+                default: dst[j] = (float)x0 * d + m; dst[j + 16] = (float)x1 * d + m; break;
+            }
+        }
+    }
+}
+
 bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
     File fp;
     fp.f = fopen(path.c_str(), "rb");
@@ -108,7 +153,10 @@ bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
         err = "unsupported context sizes";
         return false;
     }
-    if (hp.ftype != 0 && hp.ftype != 1) { err = "unsupported ftype (quantised files are out of scope, SURVEY.md §8f N2)"; return false; }
+    {   // whisper.cpp file types: 0 f32, 1 f16, 2 q4_0, 3 q4_1, 7 q8_0, 8 q5_0, 9 q5_1 (+ 1000 * quantisation version)
+        const int ft = hp.ftype % 1000;
+        if (ft != 0 && ft != 1 && ft != 2 && ft != 3 && ft != 7 && ft != 8 && ft != 9) { err = "unsupported ftype " + std::to_string(hp.ftype); return false; }
+    }
     switch (hp.n_audio_layer) {
         case 4: m.mtype = 1; break;
         case 6: m.mtype = 2; break;
@@ -168,12 +216,14 @@ bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
 
     // tensors until EOF
     std::vector<uint16_t> half;
+    std::vector<uint8_t> raw;
     while (true) {
         int32_t n_dims = 0, name_len = 0, ttype = 0;
         if (fread(&n_dims, 1, 4, fp.f) != 4) break;  // clean EOF
         if (!fp.read(&name_len, 4) || !fp.read(&ttype, 4)) { err = "truncated tensor header"; return false; }
         if (n_dims < 1 || n_dims > 4 || name_len <= 0 || name_len > 512) { err = "corrupt tensor header"; return false; }
-        if (ttype != 0 && ttype != 1) { err = "unsupported tensor type " + std::to_string(ttype); return false; }
+        const int qblock = quant_block_bytes(ttype);   // ggml block formats: 32 weights per block
+        if (ttype != 0 && ttype != 1 && qblock == 0) { err = "unsupported tensor type " + std::to_string(ttype); return false; }
         int32_t ne[4] = {1, 1, 1, 1};
         size_t count = 1;
         for (int i = 0; i < n_dims; ++i) {
@@ -186,7 +236,13 @@ bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
         t.ttype = ttype;
         for (int i = n_dims - 1; i >= 0; --i) t.shape.push_back(ne[i]);  // file stores innermost first
         t.data.resize(count);
-        if (ttype == 0) {
+        if (qblock) {
+            // quantised matrix (the catalogue's q5_0 / q5_1 / q8_0 files, reference model.rs:155-186): widened on load
+            if (ne[0] % 32 != 0) { err = "quantised tensor with a row length that is not a multiple of 32: " + name; return false; }
+            raw.resize(count / 32 * (size_t)qblock);
+            if (!fp.read(raw.data(), raw.size())) { err = "truncated tensor data: " + name; return false; }
+            dequantize_blocks(ttype, raw.data(), count / 32, t.data.data());
+        } else if (ttype == 0) {
             if (!fp.read(t.data.data(), count * 4)) { err = "truncated tensor data: " + name; return false; }
         } else {
             half.resize(count);

@@ -31,7 +31,7 @@ struct Vocab {
 struct HostTensor {
     std::vector<int64_t> shape;  // torch order (outermost first)
     std::vector<float> data;     // always widened to f32 on the host
-    int ttype = 0;               // on-disk type (0 f32, 1 f16)
+    int ttype = 0;               // on-disk ggml type (0 f32, 1 f16, 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0)
 };
 
 struct HostModel {

@@ -219,9 +219,84 @@ _F32_NAMES = (
 )
 
 
+# whisper.cpp `quantize` file types -> ggml tensor type of the quantised matrices (reference catalogue: model.rs:155-186)
+QUANT_TTYPE = {2: 2, 3: 3, 7: 8, 8: 6, 9: 7}   # ftype: q4_0, q4_1, q8_0, q5_0, q5_1
+
+
+def quantize_blocks(w: np.ndarray, ttype: int) -> bytes:
+    """ggml reference quantisers (quantize_row_q{4_0,4_1,5_0,5_1,8_0}_ref): 32 weights per block."""
+    x = np.ascontiguousarray(w, dtype=np.float32).reshape(-1, 32)
+    nb = x.shape[0]
+    if ttype == 8:
+        amax = np.abs(x).max(axis=1)
+        d = (amax / np.float32(127.0)).astype(np.float32)
+        inv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), np.float32(0)).astype(np.float32)
+        q = np.rint(x * inv[:, None]).astype(np.int8)
+        out = np.zeros((nb, 34), np.uint8)
+        out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q.view(np.uint8)
+        return out.tobytes()
+    sym = ttype in (2, 6)
+    levels = 16 if ttype in (2, 3) else 32
+    if sym:
+        idx = np.abs(x).argmax(axis=1)
+        mx = x[np.arange(nb), idx]                      # the value with the largest magnitude, sign kept
+        d = (mx / np.float32(-(levels // 2))).astype(np.float32)
+        inv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), np.float32(0)).astype(np.float32)
+        q = np.minimum(levels - 1, (x * inv[:, None] + np.float32(levels // 2 + 0.5)).astype(np.int32)).astype(np.uint8)
+        hdr = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+    else:
+        mn, mx = x.min(axis=1), x.max(axis=1)
+        d = ((mx - mn) / np.float32(levels - 1)).astype(np.float32)
+        inv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), np.float32(0)).astype(np.float32)
+        q = np.minimum(levels - 1, ((x - mn[:, None]) * inv[:, None] + np.float32(0.5)).astype(np.int32)).astype(np.uint8)
+        hdr = np.concatenate([d.astype(np.float16).view(np.uint8).reshape(nb, 2), mn.astype(np.float16).view(np.uint8).reshape(nb, 2)], axis=1)
+    qs = (q[:, :16] & 15) | ((q[:, 16:] & 15) << 4)
+    parts = [hdr]
+    if levels == 32:
+        bits = ((q >> 4) & 1).astype(np.uint32)
+        qh = (bits << np.arange(32, dtype=np.uint32)[None, :]).sum(axis=1).astype(np.uint32)
+        parts.append(qh.view(np.uint8).reshape(nb, 4))
+    parts.append(qs.astype(np.uint8))
+    return np.concatenate(parts, axis=1).tobytes()
+
+
+def dequantize_blocks(raw: bytes, ttype: int, count: int) -> np.ndarray:
+    """ggml dequantize_row_q*: the float32 values a loader must produce from `raw` (used by the tests)."""
+    bs = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}[ttype]
+    b = np.frombuffer(raw, np.uint8).reshape(-1, bs)
+    nb = b.shape[0]
+    d = b[:, 0:2].copy().view(np.float16).astype(np.float32).reshape(nb)
+    off = 2
+    m = np.zeros(nb, np.float32)
+    if ttype in (3, 7):
+        m = b[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(nb)
+        off = 4
+    if ttype == 8:
+        return (b[:, 2:].copy().view(np.int8).astype(np.float32) * d[:, None]).reshape(-1)[:count]
+    hi_bits = np.zeros((nb, 32), np.int32)
+    if ttype in (6, 7):
+        qh = b[:, off:off + 4].copy().view(np.uint32).reshape(nb)
+        hi_bits = ((qh[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.int32) << 4
+        off += 4
+    qs = b[:, off:off + 16].astype(np.int32)
+    q = np.concatenate([qs & 15, qs >> 4], axis=1) | hi_bits
+    if ttype == 2:
+        q = q - 8
+    if ttype == 6:
+        q = q - 16
+    y = q.astype(np.float32) * d[:, None]
+    if ttype in (3, 7):
+        y = y + m[:, None]
+    return y.reshape(-1)[:count]
+
+
 def write_model(path: str, arch: str | Arch, seed: int = 0, ftype: int = 0, vocab: list[bytes] | None = None,
-                init: str = "survey") -> str:
-    """Write `ggml-<arch>.bin`-layout file.  ftype 0 = all f32, 1 = f16 matrices."""
+                init: str = "survey", dequantized: bool = False) -> str:
+    """Write `ggml-<arch>.bin`-layout file.  ftype 0 = all f32, 1 = f16 matrices, 2/3/7/8/9 = q4_0/q4_1/q8_0/q5_0/q5_1
+    2-D `*.weight` matrices (what whisper.cpp's `quantize` tool produces) with the remaining tensors as for ftype 1.
+    dequantized=True writes the SAME model with every quantised matrix replaced by its float32 dequantisation
+    (the file a loader must treat identically: the parity tests compare the two)."""
     a = ARCHS[arch] if isinstance(arch, str) else arch
     vocab = vocab if vocab is not None else synthetic_vocab()
     tmp = path + ".tmp"
@@ -241,25 +316,29 @@ def write_model(path: str, arch: str | Arch, seed: int = 0, ftype: int = 0, voca
             f.write(struct.pack("<I", len(t)))
             f.write(t)
         for name, w in generate_weights(a, seed, init):
-            use_f16 = ftype == 1 and w.ndim >= 2 and name not in _F32_NAMES
+            use_f16 = ftype >= 1 and w.ndim >= 2 and name not in _F32_NAMES
+            qt = QUANT_TTYPE.get(ftype, 0) if (w.ndim == 2 and name.endswith("weight") and w.shape[-1] % 32 == 0) else 0
             nb = name.encode()
-            f.write(struct.pack("<3i", w.ndim, len(nb), 1 if use_f16 else 0))
+            if qt and dequantized:
+                w = dequantize_blocks(quantize_blocks(w, qt), qt, w.size).reshape(w.shape)
+                qt, use_f16 = 0, False
+            f.write(struct.pack("<3i", w.ndim, len(nb), qt if qt else (1 if use_f16 else 0)))
             f.write(struct.pack(f"<{w.ndim}i", *reversed(w.shape)))
             f.write(nb)
-            f.write((w.astype(np.float16) if use_f16 else w).tobytes())
+            f.write(quantize_blocks(w, qt) if qt else (w.astype(np.float16) if use_f16 else w).tobytes())
     os.replace(tmp, path)
     return path
 
 
-def model_path(dirname: str, arch: str, seed: int = 0, ftype: int = 0, init: str = "survey") -> str:
+def model_path(dirname: str, arch: str, seed: int = 0, ftype: int = 0, init: str = "survey", dequantized: bool = False) -> str:
     """Path following the reference naming `ggml-<id>.bin` (lib.rs:29), tagged by seed/ftype/init."""
     tag = "" if (seed == 0 and ftype == 0 and init == "survey") else f"-s{seed}-f{ftype}-{init}"
-    return os.path.join(dirname, f"ggml-{arch}{tag}.bin")
+    return os.path.join(dirname, f"ggml-{arch}{tag}{'-deq' if dequantized else ''}.bin")
 
 
-def ensure_model(dirname: str, arch: str, seed: int = 0, ftype: int = 0, init: str = "survey") -> str:
+def ensure_model(dirname: str, arch: str, seed: int = 0, ftype: int = 0, init: str = "survey", dequantized: bool = False) -> str:
     os.makedirs(dirname, exist_ok=True)
-    p = model_path(dirname, arch, seed, ftype, init)
+    p = model_path(dirname, arch, seed, ftype, init, dequantized)
     if not os.path.exists(p):
-        write_model(p, arch, seed, ftype, init=init)
+        write_model(p, arch, seed, ftype, init=init, dequantized=dequantized)
     return p

@@ -175,13 +175,39 @@ bool load_model(const char* path, Model& m, std::string& err) {
         int32_t nd, nl, tt;
         if (!rd(&nd, 4)) break;
         rd(&nl, 4); rd(&tt, 4);
-        if (nd < 1 || nd > 4 || nl <= 0 || nl > 256 || (tt != 0 && tt != 1)) { err = "bad tensor header"; fclose(f); return false; }
+        // ggml block formats (32 weights per block): type -> bytes per block
+        const int qbytes = tt == 2 ? 18 : tt == 3 ? 20 : tt == 6 ? 22 : tt == 7 ? 24 : tt == 8 ? 34 : 0;
+        if (nd < 1 || nd > 4 || nl <= 0 || nl > 256 || (tt != 0 && tt != 1 && !qbytes)) { err = "bad tensor header"; fclose(f); return false; }
         size_t ne = 1;
         for (int i = 0; i < nd; ++i) { int32_t d; rd(&d, 4); ne *= (size_t)d; }
         std::string name(nl, '\0');
         rd(&name[0], nl);
         Vec d(ne);
-        if (tt == 0) { if (!rd(d.data(), ne * 4)) { err = "truncated tensor"; fclose(f); return false; } }
+        if (qbytes) {
+            // dequantise as ggml's dequantize_row_q{4_0,4_1,5_0,5_1,8_0}: y = q * d (+ m), low nibbles first, fifth bits in qh
+            std::vector<uint8_t> raw(ne / 32 * (size_t)qbytes);
+            if (ne % 32 || !rd(raw.data(), raw.size())) { err = "truncated tensor"; fclose(f); return false; }
+            for (size_t b = 0; b < ne / 32; ++b) {
+                const uint8_t* p = raw.data() + b * qbytes;
+                float* y = d.data() + b * 32;
+                uint16_t h16; memcpy(&h16, p, 2); p += 2;
+                const float dd = f16_to_f32(h16);
+                float mm = 0.0f;
+                if (tt == 3 || tt == 7) { memcpy(&h16, p, 2); p += 2; mm = f16_to_f32(h16); }
+                if (tt == 8) { for (int j = 0; j < 32; ++j) y[j] = (float)(int8_t)p[j] * dd; continue; }
+                uint32_t qh = 0;
+                if (tt == 6 || tt == 7) { memcpy(&qh, p, 4); p += 4; }
+                for (int j = 0; j < 16; ++j) {
+                    int lo = p[j] & 15, hi = p[j] >> 4;
+                    if (tt == 6 || tt == 7) { lo |= ((qh >> j) & 1) << 4; hi |= ((qh >> (j + 16)) & 1) << 4; }
+                    if (tt == 2) { lo -= 8; hi -= 8; }
+                    if (tt == 6) { lo -= 16; hi -= 16; }
+                    y[j] = (float)lo * dd + mm;
+                    y[j + 16] = (float)hi * dd + mm;
+                }
+            }
+        }
+        else if (tt == 0) { if (!rd(d.data(), ne * 4)) { err = "truncated tensor"; fclose(f); return false; } }
         else {
             std::vector<uint16_t> h(ne);
             if (!rd(h.data(), ne * 2)) { err = "truncated tensor"; fclose(f); return false; }
