@@ -300,7 +300,7 @@ def main():
         peak = peaks["tf_sustained"]
         attn_tf = attn_flops_per_window(arch) * agg_dev["windows"] / (agg_dev["attn_ms"] / 1e3) / 1e12 if agg_dev["attn_ms"] > 0 else 0.0
         cpu_baseline = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the reported CPU baseline is an N = 1 figure
             from oracle import oracle
             orc = oracle.Oracle(path)
             prm = oracle.reference_params("en")

@@ -31,11 +31,6 @@ constexpr int CA_MAX_KEYS = kWinRows;
 constexpr int CA_MAX_WARPS = 16;
 constexpr int ca_smem_bytes(int stages, int warps) { return stages * CA_CHUNK_BYTES + CA_MAX_KEYS * 4 + warps * 64 * 4 + 2 * CA_MAX_WARPS * 4 + 2 * stages * 8 + 128; }
 
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
@@ -243,12 +238,6 @@ __device__ __forceinline__ float tmem_ld_1(uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
     return __uint_as_float(v);
 }
-__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint64_t policy) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "l"(policy)
-                 : "memory");
-}
 
 // SP: TMEM column pitch between the score blocks of consecutive chunks.  16 = disjoint blocks (256 columns
 // allocated); 4 = overlapping blocks written in increasing order, each MMA's don't-care columns are overwritten by
@@ -257,7 +246,7 @@ template <int TC_STAGES, int SP>
 __global__ void __launch_bounds__(192, 1)
 dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const RowDesc* __restrict__ rows, int n_items, int n_head,
                               const bf16* __restrict__ q, int ldq, bf16* __restrict__ out, int ldo, long long k_row0, long long v_row0,
-                              long long slot_rows, int n_keys, int* __restrict__ sched) {
+                              long long slot_rows, int n_keys, int* __restrict__ sched, CrossQPartials qp) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     uint8_t* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -382,8 +371,20 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
         trace_end(trace_begin(104, out));
         auto put_q = [&](int item, int buf) {   // 128 bytes of q -> row 0 of the q tile (row 0 of a swizzle atom is stored linearly)
             if (warp == 0) {
-                if (lane < 8) {
-                    const int r = item / n_head, h = item - r * n_head;
+                const int r = item / n_head, h = item - r * n_head;
+                if (qp.partial) {
+                    // q is still the split-K partial sums of the query projection: finish it here (fixed split order,
+                    // + bias) instead of in a separate epilogue launch; lane -> dims 2*lane, 2*lane + 1
+                    const float* src = qp.partial + (size_t)r * qp.ld + h * 64 + 2 * lane;
+                    float2 acc = make_float2(0.f, 0.f);
+                    for (int sp = 0; sp < qp.splits; ++sp) {
+                        const float2 t = __ldcg(reinterpret_cast<const float2*>(src + (size_t)sp * qp.plane));
+                        acc.x += t.x; acc.y += t.y;
+                    }
+                    if (qp.bias) { acc.x += __ldg(qp.bias + h * 64 + 2 * lane); acc.y += __ldg(qp.bias + h * 64 + 2 * lane + 1); }
+                    const __nv_bfloat162 hv = __floats2bfloat162_rn(acc.x, acc.y);
+                    *reinterpret_cast<__nv_bfloat162*>(sQ + buf * 2048 + lane * 4) = hv;
+                } else if (lane < 8) {
                     const uint4 v = *reinterpret_cast<const uint4*>(q + (size_t)r * ldq + h * 64 + lane * 8);
                     *reinterpret_cast<uint4*>(sQ + buf * 2048 + lane * 16) = v;
                 }
@@ -497,7 +498,7 @@ namespace {
 int env_or(const char* name, int dflt);
 template <int STAGES, int SP>
 bool launch_tc(const CUtensorMap& tm, const RowDesc* rows, int n_items, int n_head, const bf16* q, int ldq, bf16* out, int ldo, long long k_row0,
-               long long v_row0, long long slot_rows, int n_keys, int* sched, int grid, cudaStream_t s) {
+               long long v_row0, long long slot_rows, int n_keys, int* sched, const CrossQPartials& qp, int grid, cudaStream_t s) {
     constexpr int SMEM = tc_smem_bytes(STAGES);
     static bool configured = false;
     if (!configured) {
@@ -508,14 +509,17 @@ bool launch_tc(const CUtensorMap& tm, const RowDesc* rows, int n_items, int n_he
         configured = true;
     }
     launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo, k_row0,
-                  v_row0, slot_rows, n_keys, sched);
+                  v_row0, slot_rows, n_keys, sched, qp);
     return true;
 }
 }  // namespace
 
 bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
-                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s) {
+                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s,
+                                         const CrossQPartials* qpart) {
     if (n_rows <= 0) return true;
+    const CrossQPartials qp = qpart ? *qpart : CrossQPartials{};
+    if ((!q && !qp.partial) || (qp.partial && ((qp.ld & 1) || (qp.plane & 1)))) { sm100_set_error("cross attention (tc): no query"); return false; }
     if (!sched || n_keys <= 0 || n_keys > CA_MAX_KEYS || (ldq % 8) != 0 || (slot_stride % 64) || (k_off % 64) || (v_off % 64) || pool_elems / 64 >= (1ull << 31)) {
         sm100_set_error("cross attention (tc): unsupported shape");
         return false;
@@ -543,7 +547,7 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
     int grid = n_items < sms * per_sm ? n_items : sms * per_sm;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     bool ok = false;
-#define TC_CASE(S, P) if (stages == S && sp == P) ok = launch_tc<S, P>(tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, grid, s); else
+#define TC_CASE(S, P) if (stages == S && sp == P) ok = launch_tc<S, P>(tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, qp, grid, s); else
     TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(2, 4) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
     { sm100_set_error("cross attention (tc): unsupported NOBS_WHISPER_CROSS_STAGES / _SPACING"); return false; }
 #undef TC_CASE

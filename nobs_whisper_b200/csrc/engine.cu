@@ -357,6 +357,7 @@ public:
         float* x = nullptr;
         T *y = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *ys = nullptr;
         float* logits = nullptr;
+        float* probs = nullptr;           // [S][n_vocab] filtered probabilities of the last round (K6 scratch)
         float* partial = nullptr;
         int* sched = nullptr;             // 2 x (work, exit) counters of the streaming cross-attention kernel: consecutive
         unsigned cross_seq = 0;           // launches alternate, a launch may start its prologue while the previous one drains
@@ -491,16 +492,31 @@ public:
                 e.bias = L.bo; e.x = Ln.x; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = Ln.y;
                 if (!proj(Ln.att, d, L.wo, d, e)) return false;
             }
-            {   // cross-attention query
-                SkinnyEpilogue e;
-                e.bias = L.bcq; e.out = Ln.qkv; e.out_ld = d;
-                if (!proj(y, d, L.wcq, d, e)) return false;
-            }
             const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
             const T* cv = ck + cross_kv;
             const bool timed = profiling && (l % kCrossSample) == 0;
-            mark_begin(Ln.tm, timed || detail_);
-            if (!cross_attention(Ln, drows, R, Ln.qkv, d, ck, cv, Ln.att, cross_slot, cross_head)) return false;
+            if (cross_mode_ == 2 && fuse_cross_q_) {
+                // cross-attention query: split-K GEMM only; the attention kernel sums the partials (+ bias) itself
+                int splits = 0;
+                mark_begin(Ln.tm, detail_);
+                if (!launch_gemm_skinny_bf16_sm100(y, d, reinterpret_cast<const bf16*>(L.wcq), d, Ln.partial, R, d, d, &splits, st)) return gemm_fail();
+                mark_end(Ln.tm, detail_, 10);
+                CrossQPartials qp;
+                qp.partial = Ln.partial; qp.splits = splits; qp.plane = (size_t)R * d; qp.ld = d; qp.bias = L.bcq;
+                mark_begin(Ln.tm, timed || detail_);
+                if (!launch_dec_cross_attention_tc_sm100(drows, R, nullptr, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
+                                                         (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
+                                                         cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
+                    return gemm_fail();
+            } else {
+                {   // cross-attention query
+                    SkinnyEpilogue e;
+                    e.bias = L.bcq; e.out = Ln.qkv; e.out_ld = d;
+                    if (!proj(y, d, L.wcq, d, e)) return false;
+                }
+                mark_begin(Ln.tm, timed || detail_);
+                if (!cross_attention(Ln, drows, R, Ln.qkv, d, ck, cv, Ln.att, cross_slot, cross_head)) return false;
+            }
             if (timed) { mark_end(Ln.tm, true, 2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out projection + residual + MLP LayerNorm
                 SkinnyEpilogue e;
@@ -610,7 +626,7 @@ public:
             mark_begin(Ln.tm, detail_);
             launch_layernorm_gather<T>(Ln.x, d, didx, dec_ln_g_, dec_ln_b_, Ln.ys, d, S, d, st);
             { Epilogue e; if (!gemm(Ln.ys, d, tok_emb_, d, Ln.logits, hp_.n_vocab, S, hp_.n_vocab, d, e, st)) return gemm_fail(); }
-            launch_process_logits(Ln.logits, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, nullptr, st);
+            launch_process_logits(Ln.logits, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, Ln.probs, st);
             mark_end(Ln.tm, detail_, 15);
             CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, st));
             if (logits_host)
@@ -972,6 +988,7 @@ private:
         use_skinny_ = env_int("NOBS_WHISPER_SKINNY", 1) != 0;
         detail_ = env_int("NOBS_WHISPER_PROFILE_DECODE", 0) != 0;
         cross_mode_ = env_int("NOBS_WHISPER_CROSS_MODE", 2);
+        fuse_cross_q_ = env_int("NOBS_WHISPER_FUSE_CROSS_Q", 1) != 0;
         cross_ctas_ = env_int("NOBS_WHISPER_CROSS_CTAS", 0);
         const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 2)));
         // The encoder and every decode lane own their activations: a lane may decode while the encoder
@@ -997,6 +1014,7 @@ private:
             L.sched = (int*)a.take(256);
             L.ys = (T*)a.take(S * d * sizeof(T));
             L.logits = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
+            L.probs = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
         };
         lanes_.assign(n_lanes, Lane());
         Arena sizing;
@@ -1066,6 +1084,7 @@ private:
     bool use_skinny_ = true;
     int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
     int cross_ctas_ = 0;              // > 0: cap that kernel's grid
+    bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
     double host_issue_ms_ = 0, host_wait_ms_ = 0;  // decode_chunk: time spent issuing launches vs waiting for the GPU
     double detail_ms_[8] = {};

@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -225,7 +226,7 @@ constexpr int kSkinnyStages = 3;
 template <int BN>
 __global__ void __launch_bounds__(256, 2)
 gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ partial, int R,
-                         int N, int K, int kb_per_split) {
+                         int N, int K, int kb_per_split, int w_keep) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int STAGES = kSkinnyStages;   // a CTA only sees a few k-blocks: shallow ring, two CTAs fit per SM
@@ -265,10 +266,13 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
         // The weights do not depend on the previous kernel: fill the ring with weight tiles first, and only
         // then wait for the predecessor (PDL) before fetching the activations it produced.
         const int pre = min(STAGES, kb1 - kb0);
+        // decoder weights are re-read by every decode lane within a fraction of a layer time: keep them in L2
+        // (the cross-KV stream next to them is evict_first)
+        const uint64_t w_policy = w_keep ? l2_evict_last_policy() : l2_evict_normal_policy();
         if (lane == 0) {
             for (int i = 0; i < pre; ++i) {
                 mbar_expect_tx(&full[i], STAGE_BYTES);
-                tma_load_2d(sA + i * A_BYTES, &tmap_w, &full[i], (kb0 + i) * BK, m_blk * BM);
+                tma_load_2d_hint(sA + i * A_BYTES, &tmap_w, &full[i], (kb0 + i) * BK, m_blk * BM, w_policy);
             }
         }
         pdl_wait();
@@ -283,7 +287,7 @@ gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gri
             mbar_wait(&empty[stage], phase ^ 1);
             if (lane == 0) {
                 mbar_expect_tx(&full[stage], STAGE_BYTES);
-                tma_load_2d(sA + stage * A_BYTES, &tmap_w, &full[stage], kb * BK, m_blk * BM);
+                tma_load_2d_hint(sA + stage * A_BYTES, &tmap_w, &full[stage], kb * BK, m_blk * BM, w_policy);
                 tma_load_2d(sB + stage * B_BYTES, &tmap_x, &full[stage], kb * BK, 0);
             }
             __syncwarp();
@@ -437,7 +441,8 @@ bool launch_skinny_cfg(const bf16* X, int ldx, const bf16* W, int ldw, float* pa
         configured = true;
     }
     dim3 grid((N + BM - 1) / BM, splits);
-    launch_kernel(gemm_skinny_sm100_kernel<BN>, grid, dim3(256), (size_t)SMEM, s, true, tw, tx, partial, R, N, K, kb_per_split);
+    static const int w_keep = [] { const char* v = getenv("NOBS_WHISPER_W_EVICT_LAST"); return (v && *v == '1') ? 1 : 0; }();
+    launch_kernel(gemm_skinny_sm100_kernel<BN>, grid, dim3(256), (size_t)SMEM, s, true, tw, tx, partial, R, N, K, kb_per_split, w_keep);
     count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { g_err = std::string("skinny gemm launch: ") + cudaGetErrorString(err); return false; }

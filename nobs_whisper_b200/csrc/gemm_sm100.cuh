@@ -26,8 +26,18 @@ bool launch_dec_cross_attention_sm100(const RowDesc* rows, int n_rows, const bf1
 // the element offsets of this layer's K / V panels inside an audio slot, head panels 1536 x 64 apart.  `sched`: two
 // zero-initialised device ints owned by the calling stream (work counter + exit counter; the kernel re-arms them).
 // Back-to-back launches on one stream must alternate between two such pairs (a launch's prologue may overlap its predecessor).
+// Optional: the queries as the split-K partial sums of the query projection (partial[split][row][ld], + bias), summed by
+// the attention kernel itself — saves the projection's epilogue launch on the decoder's latency chain.
+struct CrossQPartials {
+    const float* partial = nullptr;
+    int splits = 0;
+    size_t plane = 0;   // floats between consecutive splits (rows * ld)
+    int ld = 0;
+    const float* bias = nullptr;
+};
 bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
-                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s);
+                                         size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s,
+                                         const CrossQPartials* qpart = nullptr);
 const char* sm100_last_error();
 
 }  // namespace nobs

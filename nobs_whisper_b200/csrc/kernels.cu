@@ -657,12 +657,12 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
 // Causal self-attention over the (short) self-KV panel: one 4-warp block per (row, head), the keys interleaved
 // over the warps (16-byte lanes as above), so the longest sequence of a step batch costs a quarter of a
 // warp-per-head pass: this kernel sits on the latency chain of every decoder layer.
-constexpr int SA_WARPS = 2;   // R x heads blocks of 64 threads stay one wave at R = 128 (4 warps: 2400 x 128 threads spill into a second wave)
+constexpr int SA_WARPS = 4;
 template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
                                                                           const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out,
                                                                           int ldo, int n_head, size_t slot_stride, size_t head_stride) {
-    constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 4;
+    constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 8;
     __shared__ float sc[448];
     __shared__ float red[2 * SA_WARPS];
     __shared__ float part[SA_WARPS][64];
@@ -918,19 +918,29 @@ template void launch_skinny_reduce<float>(const SkinnyEpilogue&, cudaStream_t);
 // K6: logit filter + log-softmax + timestamp rule + argmax / sample / top-k, one block per row.
 // Restates the reference path's per-step logit processing.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool token_suppressed(int i, const SampleParams& p, const VocabIds& v) {
-    if (p.suppress_blank && p.is_initial && (i == v.eot || i == v.blank)) return true;
+// The suppression rules of one sampling step, folded into ranges once per row (text ids are 97 % of the vocabulary
+// and only need two comparisons).  Special tokens all sit at or above eot.
+struct SuppressCtx {
+    bool first_step_blank;   // suppress_blank on the first step: eot and " "
+    bool text_forbidden;     // last token opened a timestamp pair: only a timestamp may follow
+    bool ts_forbidden;       // no_timestamps, or the last two tokens were timestamps
+    int ts_lo, ts_hi;        // timestamps outside [ts_lo, ts_hi) are suppressed
+};
+__device__ __forceinline__ SuppressCtx make_suppress_ctx(const SampleParams& p, const VocabIds& v) {
+    SuppressCtx c;
+    c.first_step_blank = p.suppress_blank && p.is_initial;
+    c.text_forbidden = p.last_was_ts && !p.penult_was_ts;
+    c.ts_forbidden = p.no_timestamps || (p.last_was_ts && p.penult_was_ts);
+    c.ts_lo = p.has_ts ? max(v.beg, p.ts_min) : v.beg;
+    c.ts_hi = p.is_initial ? min(v.n_vocab, max(p.ts_initial_limit, v.beg)) : v.n_vocab;
+    return c;
+}
+__device__ __forceinline__ bool token_suppressed(int i, const SuppressCtx& c, const VocabIds& v) {
+    if (i < v.eot) return c.text_forbidden || (c.first_step_blank && i == v.blank);
+    if (i >= v.beg) return c.ts_forbidden || i < c.ts_lo || i >= c.ts_hi;
+    if (c.first_step_blank && i == v.eot) return true;
     if (i == v.not_ || i == v.sot || i == v.nosp || i == v.solm || i == v.translate || i == v.transcribe || i == v.prev) return true;
-    if (i > v.sot && i <= v.sot + v.n_lang) return true;
-    if (i >= v.beg) {
-        if (p.no_timestamps) return true;
-        if (p.last_was_ts && p.penult_was_ts) return true;
-        if (p.is_initial && i >= p.ts_initial_limit) return true;
-        if (p.has_ts && i < p.ts_min) return true;
-    } else if (p.last_was_ts && !p.penult_was_ts && i < v.eot) {
-        return true;
-    }
-    return false;
+    return i > v.sot && i <= v.sot + v.n_lang;
 }
 
 constexpr int PL_THREADS = 1024;
@@ -945,20 +955,25 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
     __shared__ int s_pick;
     __shared__ int s_chosen[kMaxTopK];
 
+    const long long tr = trace_begin(7, logits);
     pdl_wait();
-    pdl_launch_dependents();   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
+    pdl_launch_dependents();
+    trace_end(trace_begin(107, logits));   // only one kernel ahead may sit resident: parked CTAs of a long dependency chain would hold SM resources another decode lane needs
     const int row = blockIdx.x, tid = threadIdx.x;
     const SampleParams p = params[row];
+    const SuppressCtx sc = make_suppress_ctx(p, v);
     const float* lg = logits + (size_t)row * ld;
     const int n = v.n_vocab;
     const bool scaled = p.temperature > 0.0f;
+    // probabilities of pass D, re-read by the sampling passes instead of recomputing exp(logprob) three times
+    const float* pr_cache = probs_out ? probs_out + (size_t)row * n : nullptr;
 
     // pass A: maxima
     float lmax = -INFINITY, rawmax = -INFINITY;
     for (int i = tid; i < n; i += PL_THREADS) {
         const float raw = lg[i];
         rawmax = fmaxf(rawmax, raw);
-        if (!token_suppressed(i, p, v)) lmax = fmaxf(lmax, scaled ? __fdiv_rn(raw, p.temperature) : raw);
+        if (!token_suppressed(i, sc, v)) lmax = fmaxf(lmax, scaled ? __fdiv_rn(raw, p.temperature) : raw);
     }
     lmax = block_reduce(lmax, -INFINITY, OpMax(), red_f);
     rawmax = block_reduce(rawmax, -INFINITY, OpMax(), red_f);
@@ -967,13 +982,13 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
     for (int i = tid; i < n; i += PL_THREADS) {
         const float raw = lg[i];
         if (p.want_nosp) rawsum += expf(raw - rawmax);
-        if (!token_suppressed(i, p, v)) lsum += expf((scaled ? __fdiv_rn(raw, p.temperature) : raw) - lmax);
+        if (!token_suppressed(i, sc, v)) lsum += expf((scaled ? __fdiv_rn(raw, p.temperature) : raw) - lmax);
     }
     lsum = block_reduce(lsum, 0.0f, OpAddF(), red_f);
     rawsum = block_reduce(rawsum, 0.0f, OpAddF(), red_f);
     const float logsumexp = logf(lsum) + lmax;
     auto logprob_of = [&](int i) -> float {
-        if (token_suppressed(i, p, v)) return -INFINITY;
+        if (token_suppressed(i, sc, v)) return -INFINITY;
         const float l = scaled ? __fdiv_rn(lg[i], p.temperature) : lg[i];
         return l - logsumexp;
     };
@@ -1029,11 +1044,16 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
         // q_i = p_i / sum, cp = inclusive prefix sums of q, pick = first i with cp[i] >= u.
         const int chunk = (n + PL_THREADS - 1) / PL_THREADS;
         const int i0 = tid * chunk, i1 = min(n, i0 + chunk);
+        auto prob_of = [&](int i) -> double {
+            if (pr_cache) return (double)__ldcg(pr_cache + i);   // written in pass D (other threads; ordered by the block reductions' barriers)
+            const float lp = final_logprob(i);
+            return lp > -INFINITY ? (double)expf(lp) : 0.0;
+        };
         double tot = 0.0;
-        for (int i = i0; i < i1; ++i) { const float lp = final_logprob(i); tot += lp > -INFINITY ? (double)expf(lp) : 0.0; }
+        for (int i = i0; i < i1; ++i) tot += prob_of(i);
         const double total = block_reduce(tot, 0.0, OpAddD(), red_d);
         double local = 0.0;
-        for (int i = i0; i < i1; ++i) { const float lp = final_logprob(i); local += (lp > -INFINITY ? (double)expf(lp) : 0.0) / total; }
+        for (int i = i0; i < i1; ++i) local += prob_of(i) / total;
         // exclusive scan of `local` over threads
         const int lane = tid & 31, warp = tid >> 5;
         double incl = local;
@@ -1050,10 +1070,11 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
         for (int w = 0; w < warp; ++w) woff += scan_d[w];
         double cp = woff + incl - local;
         int found = INT_MAX;
-        for (int i = i0; i < i1; ++i) {
-            const float lp = final_logprob(i);
-            cp += (lp > -INFINITY ? (double)expf(lp) : 0.0) / total;
-            if (cp >= p.u) { found = i; break; }
+        if (!(cp >= p.u)) {   // otherwise the first index with cp >= u lies in an earlier thread's range
+            for (int i = i0; i < i1; ++i) {
+                cp += prob_of(i) / total;
+                if (cp >= p.u) { found = i; break; }
+            }
         }
         if (found != INT_MAX) atomicMin(&s_pick, found);
         __syncthreads();
@@ -1104,6 +1125,7 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
         }
         results[row] = r;
     }
+    trace_end(tr);
 }
 
 void launch_process_logits(const float* logits, int ld, const SampleParams* params, SampleResult* results, int n_rows, const VocabIds& v,

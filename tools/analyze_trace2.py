@@ -5,9 +5,9 @@ import numpy as np
 a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 4)
 kid, tag, t0, t1 = a[:, 0].astype(int), a[:, 1], a[:, 2].astype(np.int64), a[:, 3].astype(np.int64)
 base = t0.min(); t0 = t0 - base; t1 = t1 - base
-names = {1: "gemm_skinny", 2: "reduce", 3: "self_attn", 4: "cross_attn", 5: "gemm"}
+names = {1: "gemm_skinny", 2: "reduce", 3: "self_attn", 4: "cross_attn", 5: "gemm", 7: "process_logits"}
 rows = []
-for k in (1, 2, 3, 4):
+for k in (1, 2, 3, 4, 7):
     for tg in np.unique(tag[kid == k]):
         b = np.where((kid == k) & (tag == tg))[0]; w = np.where((kid == 100 + k) & (tag == tg))[0]
         b = b[np.argsort(t0[b])]; w = w[np.argsort(t0[w])]
