@@ -530,7 +530,7 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
-        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 4);
+        stages = env_or("NOBS_WHISPER_CROSS_STAGES", 3);
         sp = env_or("NOBS_WHISPER_CROSS_SPACING", 4);
         per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 2);
     }

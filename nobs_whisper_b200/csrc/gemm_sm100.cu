@@ -221,15 +221,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 //   (N_out/128 tiles alone would occupy 10-40 SMs); fp32 partial sums go to a workspace
 //   [split][R][N_out] and skinny_reduce_kernel (kernels.cu) sums them in a fixed order and applies
 //   bias / GELU / residual / LayerNorm / KV-cache scatter.
-constexpr int kSkinnyStages = 3;
+constexpr int kSkinnyStagesMax = 3;
+int g_skinny_stages = kSkinnyStagesMax;
 
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, 2)
 gemm_skinny_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, float* __restrict__ partial, int R,
                          int N, int K, int kb_per_split, int w_keep) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int STAGES = kSkinnyStages;   // a CTA only sees a few k-blocks: shallow ring, two CTAs fit per SM
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -424,17 +424,16 @@ bool launch_cfg(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, 
 }
 
 
-template <int BN>
+template <int BN, int STAGES>
 bool launch_skinny_cfg(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int splits, int kb_per_split,
                        cudaStream_t s) {
-    constexpr int STAGES = kSkinnyStages;
     constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
     CUtensorMap tw, tx;
     if (!make_tmap_bf16_2d(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BM)) return false;
     if (!make_tmap_bf16_2d(&tx, X, (uint64_t)K, (uint64_t)R, (uint64_t)ldx, BK, BN)) return false;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_skinny_sm100_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_skinny_sm100_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
             g_err = "cudaFuncSetAttribute(skinny smem) failed";
             return false;
         }
@@ -442,14 +441,24 @@ bool launch_skinny_cfg(const bf16* X, int ldx, const bf16* W, int ldw, float* pa
     }
     dim3 grid((N + BM - 1) / BM, splits);
     static const int w_keep = [] { const char* v = getenv("NOBS_WHISPER_W_EVICT_LAST"); return (v && *v == '1') ? 1 : 0; }();
-    launch_kernel(gemm_skinny_sm100_kernel<BN>, grid, dim3(256), (size_t)SMEM, s, true, tw, tx, partial, R, N, K, kb_per_split, w_keep);
+    launch_kernel(gemm_skinny_sm100_kernel<BN, STAGES>, grid, dim3(256), (size_t)SMEM, s, true, tw, tx, partial, R, N, K, kb_per_split, w_keep);
     count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { g_err = std::string("skinny gemm launch: ") + cudaGetErrorString(err); return false; }
     return true;
 }
+// ring depth: 3 stages, or 2 (set_skinny_gemm_stages) to shrink the footprint so that two such CTAs fit beside the
+// attention CTAs of other decode lanes
+template <int BN>
+bool launch_skinny_bn(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int splits, int kb_per_split,
+                      cudaStream_t s) {
+    if (g_skinny_stages == 2) return launch_skinny_cfg<BN, 2>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per_split, s);
+    return launch_skinny_cfg<BN, 3>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per_split, s);
+}
 
 }  // namespace
+
+void set_skinny_gemm_stages(int stages) { g_skinny_stages = stages == 2 ? 2 : kSkinnyStagesMax; }
 
 int skinny_gemm_splits(int N, int K) {
     const int m_tiles = (N + BM - 1) / BM, num_k = (K + BK - 1) / BK;
@@ -466,9 +475,9 @@ bool launch_gemm_skinny_bf16_sm100(const bf16* X, int ldx, const bf16* W, int ld
     const int splits = skinny_gemm_splits(N, K);
     const int kb_per = (num_k + splits - 1) / splits;
     *splits_out = splits;
-    if (R <= 32) return launch_skinny_cfg<32>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
-    if (R <= 64) return launch_skinny_cfg<64>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
-    return launch_skinny_cfg<128>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+    if (R <= 32) return launch_skinny_bn<32>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+    if (R <= 64) return launch_skinny_bn<64>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
+    return launch_skinny_bn<128>(X, ldx, W, ldw, partial, R, N, K, splits, kb_per, s);
 }
 
 namespace {

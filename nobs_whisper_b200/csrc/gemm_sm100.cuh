@@ -13,6 +13,8 @@ bool launch_gemm_bf16_sm100(const bf16* A, int lda, const bf16* W, int ldw, void
 // partial[split][R][N] (the workspace must hold skinny_gemm_splits(N, K) * R * N floats); the caller
 // finishes with launch_skinny_reduce (kernels.cuh).
 int skinny_gemm_splits(int N, int K);
+// shared-memory ring depth of the decoder-step GEMM: 3 (default) or 2 (engines with several decode lanes)
+void set_skinny_gemm_stages(int stages);
 bool launch_gemm_skinny_bf16_sm100(const bf16* X, int ldx, const bf16* W, int ldw, float* partial, int R, int N, int K, int* splits_out,
                                    cudaStream_t s);
 // Non-causal encoder self-attention over 1500 keys per window, head size 64.
