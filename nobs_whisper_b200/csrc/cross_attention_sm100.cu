@@ -1,17 +1,18 @@
 // Decoder cross-attention for single-token rows (bf16), the dominant HBM stream of a decoder step:
 // every (row, head) reads one contiguous 1500 x 64 K panel and one V panel (192 KB each) of the
-// head-major cross-KV pool exactly once.
+// head-major cross-KV pool exactly once.  Both kernels here are persistent and deliberately small, so that the
+// latency-bound projection kernels of ANOTHER decode lane (engine.cu) stay resident on the same SMs while the
+// stream keeps HBM busy.
 //
-// Persistent, one CTA per SM, deliberately small: 8 consumer warps + 1 producer warp, ~107 KB of shared
-// memory, so that the latency-bound projection kernels of ANOTHER decode lane (engine.cu) stay resident
-// on the same SMs while this kernel keeps HBM busy.
-//
-//   producer (1 thread): cp.async.bulk (TMA, non-tensor) of 16 KB panel chunks into a 6-deep shared-memory
-//       ring, L2 evict_first (the stream is read once per step), running ahead across (row, head) items so
-//       the softmax barriers of an item never drain the memory pipeline.  K chunks do not depend on the
-//       predecessor kernel and are requested before the programmatic-dependent-launch wait.
-//   consumers: 8 lanes x 16 B per key row (conflict-free 512-byte warp reads), scores to shared memory,
-//       block softmax, P*V with the same mapping, deterministic cross-warp sum.
+// 1. dec_cross_attention_tc_kernel (default, second half of this file): TMA tensor loads into a swizzled ring,
+//    scores and P*V on tcgen05, 4 softmax warps.  14 % of the issue slots, 128 TMEM columns, ~57 KB per CTA.
+// 2. dec_cross_attention_sm100_kernel (NOBS_WHISPER_CROSS_MODE=1, kept as the CUDA-core variant of the same
+//    stream): a producer thread issues cp.async.bulk (TMA, non-tensor) copies of 16 KB panel chunks into a
+//    shared-memory ring, L2 evict_first, running ahead across (row, head) items so the softmax barriers of an
+//    item never drain the memory pipeline; K chunks do not depend on the predecessor kernel and are requested
+//    before the programmatic-dependent-launch wait.  Consumer warps: 8 lanes x 16 B per key row (conflict-free
+//    512-byte warp reads), scores to shared memory, block softmax, P*V with the same mapping, deterministic
+//    cross-warp sum.  Ring depth / consumer warps / CTAs per SM are template parameters (sweep in profiles/).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -219,9 +220,11 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
 //                                                                 are whatever follows in shared memory:
 //                                                                 lane m of D depends on row m of A only)
 //   K/V chunks arrive through a TMA tensor map with the 128-byte swizzle the UMMA descriptors expect; V is
-//   the MN-major B operand, read in place.  All 12 score chunks of an item sit in 192 TMEM columns; 128
-//   threads (thread = TMEM lane = key within chunk) do the softmax on 12 registers each and write p as bf16.
-//   warps 0-3 softmax/output, warp 4 TMA producer, warp 5 MMA issuer.  256 TMEM columns, ~126 KB smem.
+//   the MN-major B operand, read in place.  All 12 score chunks of an item sit in TMEM (60 columns at the
+//   default pitch of 4, see SP below); 128 threads (thread = TMEM lane = key within chunk) do the softmax on 12
+//   registers each and write p as bf16 into one linear row.  Warps 0-3 softmax/output (thread 0 also hands out
+//   items from a device-wide counter), warp 4 TMA producer, warp 5 MMA issuer.  Two CTAs per SM, so that one
+//   streams while the other is in its softmax.
 constexpr int TC_P_BYTES = 4096;         // p of all 1536 keys as one linear bf16 row (3 KB used)
 constexpr int TC_Q_BYTES = 2 * 2048;     // two q tiles (double buffered across items)
 constexpr int tc_smem_bytes(int stages) { return TC_P_BYTES + TC_Q_BYTES + stages * CA_CHUNK_BYTES + 384 + 1024; }

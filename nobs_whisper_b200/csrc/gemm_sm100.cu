@@ -464,6 +464,8 @@ int skinny_gemm_splits(int N, int K) {
     const int m_tiles = (N + BM - 1) / BM, num_k = (K + BK - 1) / BK;
     int splits = num_sms() / m_tiles;                       // one wave: never more CTAs than SMs ...
     splits = std::max(1, std::min(splits, num_k / 2));      // ... and at least two k-blocks per CTA
+    static const int cap = [] { const char* v = getenv("NOBS_WHISPER_SKINNY_MAX_SPLITS"); return (v && *v) ? atoi(v) : 0; }();
+    if (cap > 0) splits = std::min(splits, cap);
     const int kb_per = (num_k + splits - 1) / splits;
     return (num_k + kb_per - 1) / kb_per;                   // no empty splits
 }
