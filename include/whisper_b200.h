@@ -379,6 +379,21 @@ int nobs_split_at_silences_with_overlap(size_t n_samples, const size_t* boundari
 /* audio.rs:467-469 split_at_silences (16 kHz) */
 int nobs_split_at_silences(size_t n_samples, const size_t* boundaries, size_t n_boundaries, size_t* ranges, size_t* n_chunks);
 
+/* Streaming capture buffer (reference audio.rs:29-244 `AudioBuffer`; used while recording, state.rs:586-605): host
+ * logic, float32 arithmetic in the reference's order.  Chunk pointers stay valid until the next take_* / free. */
+struct nobs_audio_buffer;
+float nobs_calculate_rms(const float* samples, size_t n);                                   /* audio.rs:364-370 */
+struct nobs_audio_buffer* nobs_audio_buffer_new(uint32_t sample_rate);                      /* with_sample_rate */
+void nobs_audio_buffer_free(struct nobs_audio_buffer* b);
+void nobs_audio_buffer_push_samples(struct nobs_audio_buffer* b, const float* samples, size_t n);
+int nobs_audio_buffer_has_silence_boundary(const struct nobs_audio_buffer* b);
+const float* nobs_audio_buffer_take_chunk_at_silence(struct nobs_audio_buffer* b, size_t* n);   /* NULL == None */
+const float* nobs_audio_buffer_take_forced_chunk(struct nobs_audio_buffer* b, size_t* n);       /* NULL == None */
+const float* nobs_audio_buffer_take(struct nobs_audio_buffer* b, size_t* n);
+size_t nobs_audio_buffer_len(const struct nobs_audio_buffer* b);
+size_t nobs_audio_buffer_overlap_len(const struct nobs_audio_buffer* b);
+float nobs_audio_buffer_noise_floor(const struct nobs_audio_buffer* b);
+
 /* CUDA events on the library's own stream (slots 0..7): device-side timing of whole calls */
 int whisper_b200_event_record(struct whisper_context* ctx, int slot);
 double whisper_b200_event_elapsed_ms(struct whisper_context* ctx, int slot_a, int slot_b);
@@ -403,6 +418,11 @@ int nobs_engine_transcribe(struct nobs_engine* e, const float* audio, int n, con
 /* whisper.rs:152-197 */
 int nobs_engine_transcribe_chunked(struct nobs_engine* e, const float* const* chunks, const int* n, int n_chunks, const char* language,
                                    const char* vocabulary, const char** out);
+/* state.rs:757-792: the audio left when a recording stops (16 kHz): longer than 30 s -> cut at silences
+ * (audio.rs find_silence_boundaries / split_at_silences), pieces transcribed in order with the previous text as
+ * context (parallel != 0: decoded together, data-parallel, no chaining); results joined with " " and trimmed. */
+int nobs_engine_transcribe_recording(struct nobs_engine* e, const float* audio, size_t n, const char* language, const char* vocabulary, int parallel,
+                                     const char** out);
 /* Data-parallel variant of transcribe for independent windows: no context
  * chaining; texts[i] receives pointers owned by the engine. */
 int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audios, const int* n, int n_audios, const char* language,

@@ -199,6 +199,17 @@ SIGNATURES = {
     "nobs_split_at_silences_with_overlap": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t),
                                                       C.POINTER(C.c_size_t)]),
     "nobs_split_at_silences": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "nobs_calculate_rms": (C.c_float, [fp, C.c_size_t]),
+    "nobs_audio_buffer_new": (vp, [C.c_uint32]),
+    "nobs_audio_buffer_free": (None, [vp]),
+    "nobs_audio_buffer_push_samples": (None, [vp, fp, C.c_size_t]),
+    "nobs_audio_buffer_has_silence_boundary": (C.c_int, [vp]),
+    "nobs_audio_buffer_take_chunk_at_silence": (fp, [vp, C.POINTER(C.c_size_t)]),
+    "nobs_audio_buffer_take_forced_chunk": (fp, [vp, C.POINTER(C.c_size_t)]),
+    "nobs_audio_buffer_take": (fp, [vp, C.POINTER(C.c_size_t)]),
+    "nobs_audio_buffer_len": (C.c_size_t, [vp]),
+    "nobs_audio_buffer_overlap_len": (C.c_size_t, [vp]),
+    "nobs_audio_buffer_noise_floor": (C.c_float, [vp]),
     "whisper_b200_event_record": (C.c_int, [vp, C.c_int]),
     "whisper_b200_event_elapsed_ms": (C.c_double, [vp, C.c_int, C.c_int]),
     "whisper_b200_device_count": (C.c_int, []),
@@ -210,6 +221,7 @@ SIGNATURES = {
     "nobs_engine_is_loaded": (C.c_int, [vp]),
     "nobs_engine_transcribe": (C.c_int, [vp, fp, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]),
     "nobs_engine_transcribe_chunked": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]),
+    "nobs_engine_transcribe_recording": (C.c_int, [vp, fp, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
     "nobs_engine_transcribe_batch": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
     "nobs_engine_last_error": (C.c_char_p, [vp]),
     "nobs_engine_last_stats": (C.c_int, [vp, C.POINTER(B200Stats)]),

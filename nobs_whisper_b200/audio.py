@@ -54,3 +54,65 @@ def split_at_silences_with_overlap(audio, boundaries, sample_rate: int) -> list[
 def split_at_silences(audio, boundaries) -> list[np.ndarray]:
     """audio.rs:467-469."""
     return split_at_silences_with_overlap(audio, boundaries, WHISPER_SAMPLE_RATE)
+
+
+def calculate_rms(samples) -> float:
+    """audio.rs:364-370 (host)."""
+    a = np.ascontiguousarray(samples, dtype=np.float32)
+    return float(_lib.lib().nobs_calculate_rms(_fp(a), a.size))
+
+
+class AudioBuffer:
+    """audio.rs:29-244: the streaming capture buffer (host logic of the library, csrc/host/audio_buffer.cpp)."""
+
+    def __init__(self, sample_rate: int = 48000):
+        self._L = _lib.lib()
+        self._h = self._L.nobs_audio_buffer_new(sample_rate)
+
+    @classmethod
+    def with_sample_rate(cls, sample_rate: int) -> "AudioBuffer":
+        return cls(sample_rate)
+
+    def push_samples(self, samples) -> None:
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        self._L.nobs_audio_buffer_push_samples(self._h, _fp(a), a.size)
+
+    def has_silence_boundary(self) -> bool:
+        return bool(self._L.nobs_audio_buffer_has_silence_boundary(self._h))
+
+    def _take(self, fn):
+        n = C.c_size_t(0)
+        p = fn(self._h, C.byref(n))
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
+
+    def take_chunk_at_silence(self):
+        return self._take(self._L.nobs_audio_buffer_take_chunk_at_silence)
+
+    def take_forced_chunk(self):
+        return self._take(self._L.nobs_audio_buffer_take_forced_chunk)
+
+    def take(self):
+        return self._take(self._L.nobs_audio_buffer_take)
+
+    def __len__(self) -> int:
+        return int(self._L.nobs_audio_buffer_len(self._h))
+
+    @property
+    def overlap_len(self) -> int:
+        return int(self._L.nobs_audio_buffer_overlap_len(self._h))
+
+    def get_noise_floor(self) -> float:
+        return float(self._L.nobs_audio_buffer_noise_floor(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nobs_audio_buffer_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

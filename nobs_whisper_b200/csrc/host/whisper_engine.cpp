@@ -231,6 +231,52 @@ WhisperError WhisperEngine::transcribe_chunked(const std::vector<std::vector<flo
     return WhisperError{};
 }
 
+WhisperError WhisperEngine::transcribe_recording(const float* audio, size_t n, const std::optional<std::string>& language,
+                                                 const std::optional<std::string>& vocabulary, bool parallel, std::string& out) const {
+    out.clear();
+    if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
+    std::vector<std::pair<size_t, size_t>> pieces;
+    const size_t whisper_max_samples = 30 * 16000;   // state.rs:758
+    if (n > whisper_max_samples) {
+        std::vector<size_t> boundaries(n / 16000 + 2), ranges;
+        size_t nb = 0, nc = 0;
+        if (nobs_find_silence_boundaries(audio, n, 16000, boundaries.data(), boundaries.size(), &nb) != 0)
+            return WhisperError{WhisperError::TranscriptionError, whisper_b200_last_error()};
+        nb = std::min(nb, boundaries.size());
+        ranges.resize(2 * (nb + 1));
+        if (nobs_split_at_silences(n, boundaries.data(), nb, ranges.data(), &nc) != 0)
+            return WhisperError{WhisperError::TranscriptionError, "split_at_silences failed"};
+        for (size_t k = 0; k < nc; ++k) pieces.emplace_back(ranges[2 * k], ranges[2 * k + 1]);
+    } else {
+        pieces.emplace_back(0, n);
+    }
+    std::vector<std::string> results;
+    if (parallel && pieces.size() > 1) {
+        std::vector<const float*> ptrs;
+        std::vector<int> lens;
+        for (const auto& p : pieces) { ptrs.push_back(audio + p.first); lens.push_back((int)(p.second - p.first)); }
+        std::vector<std::string> texts;
+        WhisperError e = transcribe_batch(ptrs, lens, language, vocabulary, 0, texts);
+        if (e.kind != WhisperError::None) return e;
+        for (auto& t : texts) if (!t.empty()) results.push_back(std::move(t));
+    } else {
+        for (const auto& p : pieces) {
+            std::string text;
+            const std::optional<std::string> prev = results.empty() ? std::nullopt : std::optional<std::string>(results.back());
+            const WhisperError e = transcribe(audio + p.first, (int)(p.second - p.first), language, vocabulary, prev, text);
+            if (e.kind != WhisperError::None) continue;   // state.rs:773-775: log and go on
+            if (!text.empty()) results.push_back(std::move(text));
+        }
+    }
+    for (size_t i = 0; i < results.size(); ++i) {
+        if (i) out += " ";
+        out += results[i];
+    }
+    const size_t b = out.find_first_not_of(" \t\r\n"), e2 = out.find_last_not_of(" \t\r\n");   // .trim()
+    out = b == std::string::npos ? std::string() : out.substr(b, e2 - b + 1);
+    return WhisperError{};
+}
+
 WhisperError WhisperEngine::transcribe_batch(const std::vector<const float*>& audios, const std::vector<int>& n,
                                              const std::optional<std::string>& language, const std::optional<std::string>& vocabulary,
                                              int beam_size, std::vector<std::string>& out) const {
@@ -303,6 +349,13 @@ int nobs_engine_transcribe_chunked(struct nobs_engine* e, const float* const* ch
     std::vector<std::vector<float>> cs;
     for (int i = 0; i < n_chunks; ++i) cs.emplace_back(chunks[i], chunks[i] + std::max(0, n[i]));
     const nobs::WhisperError err = e->engine.transcribe_chunked(cs, opt(language), opt(vocabulary), e->text);
+    e->last_error = err.to_string();
+    if (out) *out = e->text.c_str();
+    return (int)err.kind;
+}
+int nobs_engine_transcribe_recording(struct nobs_engine* e, const float* audio, size_t n, const char* language, const char* vocabulary, int parallel,
+                                     const char** out) {
+    const nobs::WhisperError err = e->engine.transcribe_recording(audio, n, opt(language), opt(vocabulary), parallel != 0, e->text);
     e->last_error = err.to_string();
     if (out) *out = e->text.c_str();
     return (int)err.kind;

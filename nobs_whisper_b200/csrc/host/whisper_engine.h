@@ -45,6 +45,14 @@ public:
     WhisperError transcribe_batch(const std::vector<const float*>& audios, const std::vector<int>& n, const std::optional<std::string>& language,
                                   const std::optional<std::string>& vocabulary, int beam_size, std::vector<std::string>& out) const;
 
+    // state.rs:757-792: what the reference does with the audio left in the buffer when a recording stops — longer
+    // than 30 s: cut at silences (audio.rs find_silence_boundaries + split_at_silences), then transcribe the pieces
+    // in order, each with the previous non-empty text as context; a failing piece is skipped (state.rs:773-775),
+    // results are joined with " " and trimmed.  parallel == true decodes the pieces together instead (data-parallel,
+    // no context chaining).
+    WhisperError transcribe_recording(const float* audio, size_t n, const std::optional<std::string>& language,
+                                      const std::optional<std::string>& vocabulary, bool parallel, std::string& out) const;
+
     whisper_context* raw_context() const { return ctx_; }
     // counters of the last transcribe / transcribe_batch call, summed over its audios
     const whisper_b200_stats& last_stats() const { return last_stats_; }

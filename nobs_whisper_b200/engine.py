@@ -81,6 +81,17 @@ class WhisperEngine:
             self._raise(k)
         return (out.value or b"").decode("utf-8", errors="replace")
 
+    def transcribe_recording(self, audio, language=None, vocabulary=None, parallel: bool = False) -> str:  # state.rs:757-792
+        """The audio left when a recording stops: longer than 30 s it is cut at silences (audio.rs) and the pieces
+        are transcribed in order with the previous text as context (parallel=True: together, no chaining)."""
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        out = C.c_char_p()
+        k = self._L.nobs_engine_transcribe_recording(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), int(a.size), self._s(language),
+                                                     self._s(vocabulary), int(parallel), C.byref(out))
+        if k:
+            self._raise(k)
+        return (out.value or b"").decode("utf-8", errors="replace")
+
     def transcribe_batch(self, audios, language=None, vocabulary=None, beam_size: int = 0) -> list[str]:
         """Independent windows decoded together on the GPU; no context chaining."""
         arrs = [np.ascontiguousarray(c, dtype=np.float32) for c in audios]

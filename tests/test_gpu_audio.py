@@ -94,3 +94,25 @@ def test_chunker_feeds_the_engine(model_dir):
     batch = eng.transcribe_batch(chunks, "en", None)
     assert isinstance(chained, str) and len(batch) == len(chunks)
     eng.close()
+
+
+def test_transcribe_recording_follows_the_reference_flow(model_dir):
+    """state.rs:757-792 through the engine: > 30 s is cut at silences and chained; == the same steps done by hand."""
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import audio, ggml_synth
+    eng = nw.WhisperEngine()
+    eng.load_model(ggml_synth.ensure_model(model_dir, "micro", init="fanin"))
+    x = recording(21, 50)
+    assert len(x) > 30 * SR
+    chunks = audio.split_at_silences(x, audio.find_silence_boundaries(x, SR))
+    results = []
+    for c in chunks:                       # the loop of state.rs:764-777
+        t = eng.transcribe(c, "en", None, results[-1] if results else None)
+        if t:
+            results.append(t)
+    assert eng.transcribe_recording(x, "en", None) == " ".join(results).strip()
+    # data-parallel variant == transcribe_batch over the same pieces
+    assert eng.transcribe_recording(x, "en", None, parallel=True) == " ".join(t for t in eng.transcribe_batch(chunks, "en", None) if t).strip()
+    short = recording(22, 8)[: 8 * SR]
+    assert eng.transcribe_recording(short, "en", None) == eng.transcribe(short, "en", None, None).strip()
+    eng.close()
