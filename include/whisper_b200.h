@@ -379,6 +379,15 @@ int nobs_split_at_silences_with_overlap(size_t n_samples, const size_t* boundari
 /* audio.rs:467-469 split_at_silences (16 kHz) */
 int nobs_split_at_silences(size_t n_samples, const size_t* boundaries, size_t n_boundaries, size_t* ranges, size_t* n_chunks);
 
+/* ---- resampler (reference audio.rs:509-563 / :329-334, rubato FftFixedIn restated) ----------
+ * The block FFT resampler as one fp32 GEMM per recording on the current CUDA device; audio / out may be host or
+ * device memory.  *n_out = min(floor(n * to / from), complete blocks * block output); out == NULL only queries it. */
+int nobs_resample_audio(const float* audio, size_t n, uint32_t from_rate, uint32_t to_rate, float* out, size_t cap, size_t* n_out);
+/* audio.rs:329-334 resample_chunk: to 16 kHz, a plain copy when the input already is 16 kHz */
+int nobs_resample_chunk(const float* audio, size_t n, uint32_t input_sample_rate, float* out, size_t cap, size_t* n_out);
+/* state.rs:590-594: interleaved frames -> mono (sum of the channels / channels, float32); host */
+int nobs_mix_to_mono(const float* interleaved, size_t n_frames, uint32_t channels, float* out);
+
 /* Streaming capture buffer (reference audio.rs:29-244 `AudioBuffer`; used while recording, state.rs:586-605): host
  * logic, float32 arithmetic in the reference's order.  Chunk pointers stay valid until the next take_* / free. */
 struct nobs_audio_buffer;

@@ -199,6 +199,9 @@ SIGNATURES = {
     "nobs_split_at_silences_with_overlap": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t),
                                                       C.POINTER(C.c_size_t)]),
     "nobs_split_at_silences": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "nobs_resample_audio": (C.c_int, [fp, C.c_size_t, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "nobs_resample_chunk": (C.c_int, [fp, C.c_size_t, C.c_uint32, fp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "nobs_mix_to_mono": (C.c_int, [fp, C.c_size_t, C.c_uint32, fp]),
     "nobs_calculate_rms": (C.c_float, [fp, C.c_size_t]),
     "nobs_audio_buffer_new": (vp, [C.c_uint32]),
     "nobs_audio_buffer_free": (None, [vp]),

@@ -56,6 +56,34 @@ def split_at_silences(audio, boundaries) -> list[np.ndarray]:
     return split_at_silences_with_overlap(audio, boundaries, WHISPER_SAMPLE_RATE)
 
 
+def resample_audio(audio, from_rate: int, to_rate: int) -> np.ndarray:
+    """audio.rs:509-563 (rubato FftFixedIn(from, to, 1024, 2, 1) restated as one GEMM per recording on the GPU)."""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    n = C.c_size_t(0)
+    L = _lib.lib()
+    _check(L.nobs_resample_audio(_fp(a), a.size, from_rate, to_rate, None, 0, C.byref(n)), "resample_audio")
+    out = np.zeros(max(n.value, 1), np.float32)
+    if n.value:
+        _check(L.nobs_resample_audio(_fp(a), a.size, from_rate, to_rate, _fp(out), out.size, C.byref(n)), "resample_audio")
+    return out[: n.value]
+
+
+def resample_chunk(audio, input_sample_rate: int) -> np.ndarray:
+    """audio.rs:329-334."""
+    if input_sample_rate == WHISPER_SAMPLE_RATE:
+        return np.ascontiguousarray(audio, dtype=np.float32).copy()
+    return resample_audio(audio, input_sample_rate, WHISPER_SAMPLE_RATE)
+
+
+def mix_to_mono(interleaved, channels: int) -> np.ndarray:
+    """state.rs:590-594."""
+    a = np.ascontiguousarray(interleaved, dtype=np.float32)
+    frames = a.size // channels
+    out = np.zeros(max(frames, 1), np.float32)
+    _check(_lib.lib().nobs_mix_to_mono(_fp(a), frames, channels, _fp(out)), "mix_to_mono")
+    return out[:frames]
+
+
 def calculate_rms(samples) -> float:
     """audio.rs:364-370 (host)."""
     a = np.ascontiguousarray(samples, dtype=np.float32)

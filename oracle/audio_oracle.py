@@ -200,3 +200,71 @@ class AudioBuffer:
 
     def __len__(self):
         return int(self.samples.size)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Resampler: reference audio.rs:509-563 `resample_audio` = rubato 0.16
+# `FftFixedIn::<f32>::new(from, to, 1024, 2, 1)` fed 1024-frame chunks (last one zero-padded), output truncated to
+# floor(n * to / from).  rubato is NOT vendored in /root/reference (Cargo.lock only), so this is a restatement of
+# its published algorithm from the crate's documented design — PARITY UNPINNED beyond the reference's own test
+# (audio.rs:570-583: output length within 10 % of n/3 for 48 kHz -> 16 kHz):
+#   FftFixedIn: fft_chunks = ceil((chunk_size_in / sub_chunks) / (to / gcd)); fft_size_in/out = fft_chunks * from|to / gcd;
+#     input is buffered and every complete fft_size_in block yields fft_size_out frames (a call may yield none).
+#   FftResampler: sinc low-pass of fft_size_in taps (cutoff 0.4^(16/fft_size_in) [* out/in when decimating],
+#     Blackman-Harris^2 window, unit DC gain) scaled by 1/(2 fft_size_in); per block: zero-pad to 2 fft_size_in, real
+#     FFT, multiply the first min(fft_size_in + 1, fft_size_out) bins, inverse real FFT of 2 fft_size_out points,
+#     overlap-add the second half into the next block.
+def _rubato_sizes(fs_in: int, fs_out: int, chunk_size_in: int = 1024, sub_chunks: int = 2):
+    from math import gcd
+    g = gcd(fs_in, fs_out)
+    fft_chunks = int(np.ceil(F(chunk_size_in // sub_chunks) / F(fs_out // g)))
+    return fft_chunks * fs_in // g, fft_chunks * fs_out // g
+
+
+def _rubato_filter(n_in: int, n_out: int) -> np.ndarray:
+    """make_sincs(n_in, 1, cutoff, BlackmanHarris2)[0] in float64 (the crate computes it in f32)."""
+    cutoff = float(F(0.4) ** F(16.0 / n_in)) * (n_out / n_in if n_in > n_out else 1.0)
+    x = np.arange(n_in, dtype=np.float64)
+    xf = x / n_in
+    bh = 0.35875 - 0.48829 * np.cos(2 * np.pi * xf) + 0.14128 * np.cos(4 * np.pi * xf) - 0.01168 * np.cos(6 * np.pi * xf)
+    h = bh * bh * np.sinc((x - n_in // 2) * cutoff)
+    return h / h.sum()
+
+
+def resample_audio(audio, from_rate: int, to_rate: int) -> np.ndarray:
+    """audio.rs:509-563."""
+    x = np.asarray(audio, dtype=np.float64)
+    n = x.size
+    n_in, n_out = _rubato_sizes(from_rate, to_rate)
+    h = _rubato_filter(n_in, n_out)
+    filt = np.fft.rfft(np.concatenate([h / (2 * n_in), np.zeros(n_in)]))
+    new_len = n_in + 1 if n_in < n_out else n_out
+    padded = np.concatenate([x, np.zeros((-n) % 1024)])               # chunks of 1024, the last one zero-padded
+    n_blocks = padded.size // n_in                                    # frames left over are never flushed
+    out = np.zeros(n_blocks * n_out)
+    overlap = np.zeros(n_out)
+    for b in range(n_blocks):
+        spec = np.fft.rfft(np.concatenate([padded[b * n_in:(b + 1) * n_in], np.zeros(n_in)]))
+        o = np.zeros(n_out + 1, np.complex128)
+        o[:new_len] = spec[:new_len] * filt[:new_len]
+        o[0] = o[0].real                                              # the inverse real FFT ignores Im(DC)
+        y = np.fft.irfft(o, 2 * n_out) * (2 * n_out)                  # realfft's inverse is unnormalised
+        out[b * n_out:(b + 1) * n_out] = y[:n_out] + overlap
+        overlap = y[n_out:]
+    expected = int(n * (to_rate / from_rate))
+    return out[:expected].astype(F)
+
+
+def resample_chunk(audio, input_sample_rate: int) -> np.ndarray:
+    """audio.rs:329-334."""
+    if input_sample_rate == WHISPER_SAMPLE_RATE:
+        return np.asarray(audio, dtype=F).copy()
+    return resample_audio(audio, input_sample_rate, WHISPER_SAMPLE_RATE)
+
+
+def mix_to_mono(interleaved, channels: int) -> np.ndarray:
+    """state.rs:590-594: mono = sum of the frame's channels / channels (float32, left to right)."""
+    x = np.asarray(interleaved, dtype=F)
+    fr = x[: x.size // channels * channels].reshape(-1, channels)
+    s = np.cumsum(fr, axis=1, dtype=F)[:, -1]
+    return (s / F(channels)).astype(F)

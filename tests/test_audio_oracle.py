@@ -101,3 +101,26 @@ def test_window_rms_is_the_sequential_float32_sum():
         for v in x[i * 320:(i + 1) * 320]:
             s = np.float32(s + np.float32(v * v))
         assert r[i] == np.sqrt(np.float32(s / np.float32(320)))
+
+
+def test_resample_ratio():   # audio.rs:570-583, the reference's only test of the resampler
+    x = np.sin(np.arange(48000, dtype=np.float32) * np.float32(0.001)).astype(np.float32)
+    y = ao.resample_audio(x, 48000, 16000)
+    expected = len(x) // 3
+    assert abs(len(y) - expected) < expected // 10
+    assert len(y) == 15872        # 47 chunks of 1024 -> 31 complete 1536-frame blocks -> 31 * 512 frames
+
+
+def test_resampler_oracle_is_a_low_pass_decimator():
+    """Signal-level properties of the restated design (it cannot be pinned against rubato itself offline)."""
+    t = np.arange(96000) / 48000.0
+    for f, keep in ((440.0, True), (3000.0, True), (7000.0, True), (9000.0, False), (15000.0, False)):
+        y = ao.resample_audio(np.sin(2 * np.pi * f * t).astype(np.float32), 48000, 16000)
+        body = y[2000:-200]
+        if keep:   # same tone at 16 kHz, delayed by half the 1536-tap filter (256 output frames)
+            ref = np.sin(2 * np.pi * f * (np.arange(len(y)) - 256) / 16000.0)[2000:-200]
+            assert np.abs(body - ref).max() < 1e-4
+        else:      # above the new Nyquist: rejected, not aliased
+            assert np.abs(body).max() < 1e-5
+    assert np.array_equal(ao.resample_chunk(np.ones(5, np.float32), 16000), np.ones(5, np.float32))
+    assert np.array_equal(ao.mix_to_mono(np.array([1, 3, 2, 4], np.float32), 2), np.array([2, 3], np.float32))

@@ -116,3 +116,29 @@ def test_transcribe_recording_follows_the_reference_flow(model_dir):
     short = recording(22, 8)[: 8 * SR]
     assert eng.transcribe_recording(short, "en", None) == eng.transcribe(short, "en", None, None).strip()
     eng.close()
+
+
+@pytest.mark.parametrize("fs_in,seconds", [(48000, 1.0), (48000, 12.3), (44100, 7.7), (22050, 5.0), (8000, 3.0), (32000, 0.01)])
+def test_resampler_matches_the_oracle(fs_in, seconds):
+    """the GEMM-form block resampler against the FFT-form oracle (float32 tolerance 1e-4
+    relative to the signal peak; lengths exact, including the reference's own case audio.rs:570-583)."""
+    from nobs_whisper_b200 import audio
+    rng = np.random.default_rng(fs_in)
+    n = int(fs_in * seconds)
+    t = np.arange(n) / fs_in
+    x = (0.4 * np.sin(2 * np.pi * 220 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t + 1.0) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    got, want = audio.resample_audio(x, fs_in, 16000), ao.resample_audio(x, fs_in, 16000)
+    assert got.shape == want.shape
+    if len(want):
+        assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+    if fs_in == 48000 and seconds == 1.0:
+        assert len(got) == 15872
+
+
+def test_resample_chunk_and_mono_mix():
+    from nobs_whisper_b200 import audio
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+    assert np.array_equal(audio.resample_chunk(x, 16000), x)                      # audio.rs:330-332
+    assert np.allclose(audio.resample_chunk(x, 48000), ao.resample_chunk(x, 48000), atol=1e-4)
+    st = np.random.default_rng(1).standard_normal(2000).astype(np.float32)
+    assert np.array_equal(audio.mix_to_mono(st, 2), ao.mix_to_mono(st, 2))        # state.rs:590-594
