@@ -490,7 +490,14 @@ bool dispatch(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, in
     auto tiles = [&](int bn) { return mt * ((N + bn - 1) / bn); };
     // widest tile that still gives every SM work; skinny (decoder) problems fall to BN = 32 so that
     // the weight stream is spread over as many SMs as possible
-    if (tiles(256) >= sms) return launch_cfg<256, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    if (tiles(256) >= sms) {
+        // wave quantisation: N = 1280 at M = 12288 is 480 tiles = 3.24 waves of 148 CTAs (81 % busy); the same problem
+        // in 128-wide tiles is 6.49 waves (93 %) at ~8 % more operand traffic per FLOP
+        static const int prefer128 = [] { const char* v = getenv("NOBS_WHISPER_GEMM_WAVE_BN128"); return (v && *v == '0') ? 0 : 1; }();
+        auto eff = [&](int bn) { const int t = tiles(bn); return (double)t / (double)(((t + sms - 1) / sms) * sms); };
+        if (prefer128 && eff(128) * 0.92 > eff(256)) return launch_cfg<128, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+        return launch_cfg<256, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
+    }
     if (tiles(128) >= sms) return launch_cfg<128, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
     if (tiles(64) >= sms) return launch_cfg<64, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
     return launch_cfg<32, TC>(A, lda, W, ldw, C, ldc, M, N, K, e, s);
