@@ -283,7 +283,7 @@ enum whisper_b200_precision {
 struct whisper_context* whisper_b200_init_from_file(const char* path_model, struct whisper_context_params params, int precision);
 int whisper_b200_precision(struct whisper_context* ctx);
 /* Number of decode lanes of the context (independent stream + workspace pairs that batches are partitioned over;
- * env NOBS_WHISPER_LANES, default 3 in bf16 and 1 in fp32). */
+ * env NOBS_WHISPER_LANES, default 2 in bf16 and 1 in fp32). */
 int whisper_b200_decode_lanes(struct whisper_context* ctx);
 /* Parses the file (hparams, vocabulary, mel filters) WITHOUT touching a GPU: a handle for the
  * vocabulary / tokenizer / model-query functions only.  Every compute entry point fails on it. */

@@ -990,7 +990,7 @@ private:
         cross_mode_ = env_int("NOBS_WHISPER_CROSS_MODE", 2);
         fuse_cross_q_ = env_int("NOBS_WHISPER_FUSE_CROSS_Q", 1) != 0;
         cross_ctas_ = env_int("NOBS_WHISPER_CROSS_CTAS", 0);
-        const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 3)));
+        const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 2)));
         // with several lanes the step GEMMs run a 2-deep ring (49 KB at 64 rows): two of them fit next to the two
         // attention CTAs (2 x 57 KB) an SM holds for another lane
         set_skinny_gemm_stages(env_int("NOBS_WHISPER_SKINNY_STAGES", n_lanes > 1 ? 2 : 3));
