@@ -183,6 +183,7 @@ class WhisperContext:
     def n_text_layer(self): return _lib.lib().whisper_model_n_text_layer(self._h)
     def n_mels(self): return _lib.lib().whisper_model_n_mels(self._h)
     def precision(self): return {1: "fp32", 2: "bf16"}.get(_lib.lib().whisper_b200_precision(self._h))
+    def decode_lanes(self) -> int: return int(_lib.lib().whisper_b200_decode_lanes(self._h))
     def token_eot(self): return _lib.lib().whisper_token_eot(self._h)
     def token_sot(self): return _lib.lib().whisper_token_sot(self._h)
     def token_beg(self): return _lib.lib().whisper_token_beg(self._h)
