@@ -43,7 +43,10 @@ void prefer_max_shared_carveout(const void* kernel) {
 constexpr int kMelWarps = 4;
 
 __global__ void __launch_bounds__(kMelWarps * 32) mel_stft_kernel(MelTables t, const MelJob* __restrict__ jobs, int frames_per_block) {
-    __shared__ float2 s_tw[kNFft];
+    // Twiddles are kept as compact per-stage tables: indexing the 400-entry table with strides of 16 / 8 / 4 / 2
+    // (as the factorisation does) lands every lane of a warp on the same one or two banks.  Same values, no conflicts.
+    __shared__ float2 s_tw25[25];        // e^{-2 pi i j / 25}
+    __shared__ float2 s_tws[375];        // radix-2 stage s (L = 25 << s): entries [25 * ((1 << s) - 1) + k] = e^{-2 pi i k / (2L)}
     __shared__ float s_hann[kNFft];
     __shared__ float s_x[kMelWarps][kNFft];
     __shared__ float2 s_a[kMelWarps][kNFft];
@@ -52,9 +55,12 @@ __global__ void __launch_bounds__(kMelWarps * 32) mel_stft_kernel(MelTables t, c
     const MelJob job = jobs[blockIdx.y];
     const int f_begin = blockIdx.x * frames_per_block;
     if (f_begin >= job.n_frames) return;
-    for (int i = threadIdx.x; i < kNFft; i += blockDim.x) {
-        s_tw[i] = t.tw[i];
-        s_hann[i] = t.hann[i];
+    for (int i = threadIdx.x; i < kNFft; i += blockDim.x) s_hann[i] = t.hann[i];
+    for (int i = threadIdx.x; i < 25; i += blockDim.x) s_tw25[i] = t.tw[16 * i];
+    for (int i = threadIdx.x; i < 375; i += blockDim.x) {
+        const int stage = i < 25 ? 0 : i < 75 ? 1 : i < 175 ? 2 : 3;
+        const int k = i - 25 * ((1 << stage) - 1);
+        s_tws[i] = t.tw[k * (kNFft / (2 * (25 << stage)))];
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(kMelWarps * 32) mel_stft_kernel(MelTables t, c
 #pragma unroll 5
             for (int m = 0; m < 25; ++m) {
                 const float xv = x[16 * m + r];
-                const float2 w = s_tw[16 * ((m * k) % 25)];
+                const float2 w = s_tw25[(m * k) % 25];
                 re += xv * w.x;
                 im -= xv * w.y;
             }
@@ -104,12 +110,13 @@ __global__ void __launch_bounds__(kMelWarps * 32) mel_stft_kernel(MelTables t, c
         float2* out = B;
 #pragma unroll
         for (int stage = 0; stage < 4; ++stage) {
-            const int L = 25 << stage, halfR = 8 >> stage, step = kNFft / (2 * L);
+            const int L = 25 << stage, halfR = 8 >> stage;
+            const float2* tws = s_tws + 25 * ((1 << stage) - 1);
             for (int o = lane; o < kNFft / 2; o += 32) {
                 const int r = o / L, k = o - r * L;
                 const float2 e = in[r * L + k];
                 const float2 od = in[(r + halfR) * L + k];
-                const float2 w = s_tw[k * step];
+                const float2 w = tws[k];
                 const float tr = w.x * od.x + w.y * od.y;
                 const float ti = w.x * od.y - w.y * od.x;
                 out[r * 2 * L + k] = make_float2(e.x + tr, e.y + ti);
