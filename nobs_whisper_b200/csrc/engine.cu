@@ -453,7 +453,7 @@ public:
     // Decoder layers for a step batch of R <= 128 token rows (bf16): every projection is a swap-AB split-K
     // tcgen05 GEMM that streams its weights through all SMs, finished by one fused epilogue kernel
     // (bias / GELU / residual / next LayerNorm / KV scatter).  14 launches per layer.
-    bool decode_layers_skinny(Lane& Ln, const RowDesc* drows, int R) {
+    bool decode_layers_skinny(Lane& Ln, const RowDesc* drows, int R, bool distinct_slots) {
         const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
         cudaStream_t st = Ln.stream;
         const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
@@ -478,15 +478,29 @@ public:
             const Layer<T>& L = dec_[l];
             T* kc = self_pool_ + (size_t)l * 2 * self_kv;
             T* vc = kc + self_kv;
-            {   // QKV projection + KV-cache append
-                SkinnyEpilogue e;
-                e.bias = L.bqkv; e.out = Ln.qkv; e.out_ld = 3 * d;
-                e.rows = drows; e.kpanel = kc; e.vpanel = vc; e.slot_stride = self_slot; e.n_pos_cap = ntc; e.d = d;
-                if (!proj(y, d, L.wqkv, 3 * d, e)) return false;
+            if (fuse_qkv_ && distinct_slots) {
+                // QKV projection: split-K GEMM only; the self-attention kernel sums the partials (+ bias), appends the new
+                // key / value row to the cache and attends — one launch less on the chain.  Needs one row per KV slot.
+                int splits = 0;
+                mark_begin(Ln.tm, detail_);
+                if (!launch_gemm_skinny_bf16_sm100(y, d, reinterpret_cast<const bf16*>(L.wqkv), d, Ln.partial, R, 3 * d, d, &splits, st)) return gemm_fail();
+                mark_end(Ln.tm, detail_, 10);
+                QkvPartials qp;
+                qp.partial = Ln.partial; qp.splits = splits; qp.plane = (size_t)R * 3 * d; qp.ld = 3 * d; qp.bias = L.bqkv;
+                mark_begin(Ln.tm, detail_);
+                launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st, &qp);
+                mark_end(Ln.tm, detail_, 12);
+            } else {
+                {   // QKV projection + KV-cache append
+                    SkinnyEpilogue e;
+                    e.bias = L.bqkv; e.out = Ln.qkv; e.out_ld = 3 * d;
+                    e.rows = drows; e.kpanel = kc; e.vpanel = vc; e.slot_stride = self_slot; e.n_pos_cap = ntc; e.d = d;
+                    if (!proj(y, d, L.wqkv, 3 * d, e)) return false;
+                }
+                mark_begin(Ln.tm, detail_);
+                launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
+                mark_end(Ln.tm, detail_, 12);
             }
-            mark_begin(Ln.tm, detail_);
-            launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
-            mark_end(Ln.tm, detail_, 12);
             {   // out projection + residual + cross-attention LayerNorm
                 SkinnyEpilogue e;
                 e.bias = L.bo; e.x = Ln.x; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = Ln.y;
@@ -535,6 +549,23 @@ public:
                 if (!proj(Ln.h, 4 * d, L.w2, d, e)) return false;
             }
         }
+        return true;
+    }
+
+    // logits = ys * tok_emb^T.  For a step batch (S <= 128 sample rows, bf16) this is the same weight-streaming shape as
+    // the layer projections: the swap-AB kernel with one K split writes fp32 [S][n_vocab] directly (406 weight tiles
+    // over all SMs) instead of two ragged waves of 128 x 256 tiles.
+    bool logits_gemm(Lane& Ln, int S) {
+        const int d = d_;
+        if (skinny_logits_ && sizeof(T) == 2 && S <= 128 && skinny_gemm_splits(hp_.n_vocab, d) == 1) {
+            int splits = 0;
+            if (!launch_gemm_skinny_bf16_sm100(reinterpret_cast<const bf16*>(Ln.ys), d, reinterpret_cast<const bf16*>(tok_emb_), d, Ln.logits, S, hp_.n_vocab, d,
+                                               &splits, Ln.stream))
+                return gemm_fail();
+            return true;
+        }
+        Epilogue e;
+        if (!gemm(Ln.ys, d, tok_emb_, d, Ln.logits, hp_.n_vocab, S, hp_.n_vocab, d, e, Ln.stream)) return gemm_fail();
         return true;
     }
 
@@ -596,7 +627,14 @@ public:
         const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
         const bool skinny = use_skinny_ && sizeof(T) == 2 && R <= 128 && 4 * d <= 5120;
         if (skinny) {
-            if (!decode_layers_skinny(Ln, drows, R)) return false;
+            bool distinct = true;   // single-token steps: one row per KV slot
+            {
+                std::vector<int> slots(R);
+                for (int r = 0; r < R; ++r) slots[r] = rows[r].kv_slot;
+                std::sort(slots.begin(), slots.end());
+                distinct = std::adjacent_find(slots.begin(), slots.end()) == slots.end();
+            }
+            if (!decode_layers_skinny(Ln, drows, R, distinct)) return false;
         } else {
             for (int l = 0; l < Ld; ++l) {
                 const Layer<T>& L = dec_[l];
@@ -625,7 +663,7 @@ public:
         if (S > 0) {
             mark_begin(Ln.tm, detail_);
             launch_layernorm_gather<T>(Ln.x, d, didx, dec_ln_g_, dec_ln_b_, Ln.ys, d, S, d, st);
-            { Epilogue e; if (!gemm(Ln.ys, d, tok_emb_, d, Ln.logits, hp_.n_vocab, S, hp_.n_vocab, d, e, st)) return gemm_fail(); }
+            if (!logits_gemm(Ln, S)) return false;
             launch_process_logits(Ln.logits, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, Ln.probs, st);
             mark_end(Ln.tm, detail_, 15);
             CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, st));
@@ -989,6 +1027,8 @@ private:
         detail_ = env_int("NOBS_WHISPER_PROFILE_DECODE", 0) != 0;
         cross_mode_ = env_int("NOBS_WHISPER_CROSS_MODE", 2);
         fuse_cross_q_ = env_int("NOBS_WHISPER_FUSE_CROSS_Q", 1) != 0;
+        skinny_logits_ = env_int("NOBS_WHISPER_SKINNY_LOGITS", 1) != 0;
+        fuse_qkv_ = env_int("NOBS_WHISPER_FUSE_QKV", 1) != 0;
         cross_ctas_ = env_int("NOBS_WHISPER_CROSS_CTAS", 0);
         const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 2)));
         // with several lanes the step GEMMs run a 2-deep ring (49 KB at 64 rows): two of them fit next to the two
@@ -1087,6 +1127,8 @@ private:
     bool use_skinny_ = true;
     int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
     int cross_ctas_ = 0;              // > 0: cap that kernel's grid
+    bool fuse_qkv_ = true;            // single-token steps: the self-attention kernel finishes the QKV projection's split-K sums
+    bool skinny_logits_ = true;       // step batches: logits through the swap-AB weight-streaming GEMM
     bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
     double host_issue_ms_ = 0, host_wait_ms_ = 0;  // decode_chunk: time spent issuing launches vs waiting for the GPU

@@ -665,14 +665,21 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
 // over the warps (16-byte lanes as above), so the longest sequence of a step batch costs a quarter of a
 // warp-per-head pass: this kernel sits on the latency chain of every decoder layer.
 constexpr int SA_WARPS = 4;
+// QkvPartials (kernels.cuh): when given, q and the new key / value row of this (row, head) are still the split-K
+// partial sums of the QKV projection; the block finishes them (fixed split order, + bias), appends k / v to the cache
+// panel and attends over keys 0..pos with the new row taken from shared memory — the projection's epilogue launch is
+// gone from the latency chain.  Only valid when no two rows of the batch share a KV slot (single-token steps).
 template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
-                                                                          const T* __restrict__ kc, const T* __restrict__ vc, T* __restrict__ out,
-                                                                          int ldo, int n_head, size_t slot_stride, size_t head_stride) {
+                                                                          T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
+                                                                          int ldo, int n_head, size_t slot_stride, size_t head_stride, QkvPartials qp) {
     constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 8;
     __shared__ float sc[448];
     __shared__ float red[2 * SA_WARPS];
     __shared__ float part[SA_WARPS][64];
+    __shared__ float qs[64];
+    __shared__ __align__(16) T k_new[64];
+    __shared__ __align__(16) T v_new[64];
     const long long tr = trace_begin(3, out);
     pdl_wait();
     pdl_launch_dependents();
@@ -682,19 +689,47 @@ __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const
     const RowDesc rd = rows[r];
     const int nk = min(rd.pos + 1, 448);
     const size_t base = (size_t)rd.kv_slot * slot_stride + (size_t)h * head_stride;
-    const T* K = kc + base;
-    const T* V = vc + base;
+    T* K = kc + base;
+    T* V = vc + base;
+    const bool fused = qp.partial != nullptr;
+    const int j_new = fused ? nk - 1 : -1;    // the key row that only exists in shared memory so far
+    if (fused) {
+        const int e = tid & 63, which = tid >> 6;          // threads 0-63: q and k, 64-127: v
+        const int d = n_head * 64;
+        const float* src = qp.partial + (size_t)r * qp.ld + h * 64 + e;
+        float a = 0.0f, b = 0.0f;
+        const int off_a = which ? 2 * d : 0;
+        for (int s = 0; s < qp.splits; ++s) {
+            a += __ldcg(src + (size_t)s * qp.plane + off_a);
+            if (!which) b += __ldcg(src + (size_t)s * qp.plane + d);
+        }
+        if (qp.bias) { a += __ldg(qp.bias + off_a + h * 64 + e); if (!which) b += __ldg(qp.bias + d + h * 64 + e); }
+        if (!which) {
+            qs[e] = a;
+            const T kb = from_f32<T>(b);
+            k_new[e] = kb;
+            K[(size_t)(nk - 1) * 64 + e] = kb;
+        } else {
+            const T vb = from_f32<T>(a);
+            v_new[e] = vb;
+            V[(size_t)(nk - 1) * 64 + e] = vb;
+        }
+    } else if (tid < 64) {
+        qs[tid] = to_f32(q[(size_t)r * ldq + h * 64 + tid]);
+    }
+    __syncthreads();
     const int sub = lane % LPK, ks = warp * KPW + lane / LPK;   // key slot of this thread within a block iteration
     float qv[VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) qv[i] = to_f32(q[(size_t)r * ldq + h * 64 + sub * VN + i]);
+    for (int i = 0; i < VN; ++i) qv[i] = qs[sub * VN + i];
     float lmax = -INFINITY;
     for (int j0 = 0; j0 < nk; j0 += UNR * KPB) {
         typename Vec16<T>::Raw raw[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int j = j0 + u * KPB + ks;
-            raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+            if (j == j_new) raw[u] = *reinterpret_cast<const typename Vec16<T>::Raw*>(k_new + sub * VN);
+            else raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
@@ -740,7 +775,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int j = j0 + u * KPB + ks;
-            raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+            if (j == j_new) raw[u] = *reinterpret_cast<const typename Vec16<T>::Raw*>(v_new + sub * VN);
+            else raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
@@ -773,11 +809,13 @@ __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const
 
 template <typename T>
 void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
-                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s) {
+                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s, const QkvPartials* qkv_partials) {
     if (n_rows <= 0) return;
     if (!cross) {
         dim3 grid(n_rows, n_head);
-        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, kbase, vbase, out, ldo, n_head, slot_stride, head_stride);
+        const QkvPartials qp = qkv_partials ? *qkv_partials : QkvPartials{};
+        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, const_cast<T*>(kbase), const_cast<T*>(vbase), out, ldo,
+                      n_head, slot_stride, head_stride, qp);
         NOBS_COUNT_LAUNCH();
         return;
     }
@@ -786,9 +824,9 @@ void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, 
     NOBS_COUNT_LAUNCH();
 }
 template void launch_dec_attention<float>(const RowDesc*, int, const float*, int, const float*, const float*, float*, int, int, int, size_t, size_t,
-                                          int, cudaStream_t);
+                                          int, cudaStream_t, const QkvPartials*);
 template void launch_dec_attention<bf16>(const RowDesc*, int, const bf16*, int, const bf16*, const bf16*, bf16*, int, int, int, size_t, size_t, int,
-                                         cudaStream_t);
+                                         cudaStream_t, const QkvPartials*);
 
 // beam search: copy the first n_pos rows of every [n_pos_cap][64] panel of one self-KV slot to another
 template <typename T>

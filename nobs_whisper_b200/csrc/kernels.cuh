@@ -95,11 +95,20 @@ void launch_embed(const RowDesc* rows, int n_rows, const T* tok_emb, const float
 template <typename T>
 void launch_scatter_kv(const RowDesc* rows, int n_rows, const T* qkv, T* kpanel0, T* vpanel0, size_t slot_stride, int n_pos_cap, int d,
                        cudaStream_t s);
+// Optional input of the self-attention launch: q / k / v of the step rows as the split-K partial sums of the QKV
+// projection (partial[split][row][ld = 3d], + bias [3d]); the kernel finishes them and appends k / v to the cache.
+struct QkvPartials {
+    const float* partial = nullptr;
+    int splits = 0;
+    size_t plane = 0;   // floats between consecutive splits (rows * ld)
+    int ld = 0;
+    const float* bias = nullptr;
+};
 // one (row, head) per block; key j of head h lives at base + slot*slot_stride + h*head_stride + j*64.
 // cross == 0: slot = kv_slot, keys 0..pos (causal);  cross == 1: slot = audio_slot, keys 0..n_keys-1.
 template <typename T>
 void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, const T* kbase, const T* vbase, T* out, int ldo, int n_head,
-                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s);
+                          int cross, size_t slot_stride, size_t head_stride, int n_keys, cudaStream_t s, const QkvPartials* qkv_partials = nullptr);
 // self-KV slot copy for beam search: the first n_pos rows of each of the n_panels [n_pos_cap][64] panels
 struct KvCopy {
     int src, dst, n_pos;
