@@ -664,13 +664,13 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const RowDesc
 // Causal self-attention over the (short) self-KV panel: one 4-warp block per (row, head), the keys interleaved
 // over the warps (16-byte lanes as above), so the longest sequence of a step batch costs a quarter of a
 // warp-per-head pass: this kernel sits on the latency chain of every decoder layer.
-constexpr int SA_WARPS = 4;
+constexpr int SA_WARPS = 2;   // 128 rows x 20 heads x 64 threads at <= 64 registers is ONE resident wave; 4 warps were two waves plus a tail
 // QkvPartials (kernels.cuh): when given, q and the new key / value row of this (row, head) are still the split-K
 // partial sums of the QKV projection; the block finishes them (fixed split order, + bias), appends k / v to the cache
 // panel and attends over keys 0..pos with the new row taken from shared memory — the projection's epilogue launch is
 // gone from the latency chain.  Only valid when no two rows of the batch share a KV slot (single-token steps).
 template <typename T>
-__global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+__global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
                                                                           T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
                                                                           int ldo, int n_head, size_t slot_stride, size_t head_stride, QkvPartials qp) {
     constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 8;
@@ -694,28 +694,33 @@ __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const
     const bool fused = qp.partial != nullptr;
     const int j_new = fused ? nk - 1 : -1;    // the key row that only exists in shared memory so far
     if (fused) {
-        const int e = tid & 63, which = tid >> 6;          // threads 0-63: q and k, 64-127: v
         const int d = n_head * 64;
-        const float* src = qp.partial + (size_t)r * qp.ld + h * 64 + e;
-        float a = 0.0f, b = 0.0f;
-        const int off_a = which ? 2 * d : 0;
-        for (int s = 0; s < qp.splits; ++s) {
-            a += __ldcg(src + (size_t)s * qp.plane + off_a);
-            if (!which) b += __ldcg(src + (size_t)s * qp.plane + d);
-        }
-        if (qp.bias) { a += __ldg(qp.bias + off_a + h * 64 + e); if (!which) b += __ldg(qp.bias + d + h * 64 + e); }
-        if (!which) {
-            qs[e] = a;
-            const T kb = from_f32<T>(b);
+        for (int e = tid; e < 64; e += SA_WARPS * 32) {   // element e of q, k and v: all split-K loads of a trip in flight together
+            const float* src = qp.partial + (size_t)r * qp.ld + h * 64 + e;
+            float aq = 0.0f, ak = 0.0f, av = 0.0f;
+            for (int s0 = 0; s0 < qp.splits; s0 += 4) {
+                float tq[4], tk[4], tv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool ok = s0 + u < qp.splits;
+                    const float* p = src + (size_t)(s0 + u) * qp.plane;
+                    tq[u] = ok ? __ldcg(p) : 0.0f;
+                    tk[u] = ok ? __ldcg(p + d) : 0.0f;
+                    tv[u] = ok ? __ldcg(p + 2 * d) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { aq += tq[u]; ak += tk[u]; av += tv[u]; }   // fixed split order
+            }
+            if (qp.bias) { aq += __ldg(qp.bias + h * 64 + e); ak += __ldg(qp.bias + d + h * 64 + e); av += __ldg(qp.bias + 2 * d + h * 64 + e); }
+            qs[e] = aq;
+            const T kb = from_f32<T>(ak), vb = from_f32<T>(av);
             k_new[e] = kb;
-            K[(size_t)(nk - 1) * 64 + e] = kb;
-        } else {
-            const T vb = from_f32<T>(a);
             v_new[e] = vb;
+            K[(size_t)(nk - 1) * 64 + e] = kb;
             V[(size_t)(nk - 1) * 64 + e] = vb;
         }
-    } else if (tid < 64) {
-        qs[tid] = to_f32(q[(size_t)r * ldq + h * 64 + tid]);
+    } else {
+        for (int e = tid; e < 64; e += SA_WARPS * 32) qs[e] = to_f32(q[(size_t)r * ldq + h * 64 + e]);
     }
     __syncthreads();
     const int sub = lane % LPK, ks = warp * KPW + lane / LPK;   // key slot of this thread within a block iteration
@@ -798,11 +803,11 @@ __global__ void __launch_bounds__(SA_WARPS * 32) dec_self_attention_kernel(const
         for (int i = 0; i < VN; ++i) part[warp][sub * VN + i] = acc[i];
     }
     __syncthreads();
-    if (tid < 64) {
+    for (int e = tid; e < 64; e += SA_WARPS * 32) {
         float o = 0.0f;
 #pragma unroll
-        for (int w = 0; w < SA_WARPS; ++w) o += part[w][tid];   // fixed order
-        out[(size_t)r * ldo + h * 64 + tid] = from_f32<T>(o * inv);
+        for (int w = 0; w < SA_WARPS; ++w) o += part[w][e];   // fixed order
+        out[(size_t)r * ldo + h * 64 + e] = from_f32<T>(o * inv);
     }
     trace_end(tr);
 }
