@@ -163,4 +163,29 @@ extern "C" {
     pub fn whisper_b200_full_batch(ctx: *mut whisper_context, states: *const *mut whisper_state, n: c_int, params: whisper_full_params,
                                    samples: *const *const c_float, n_samples: *const c_int, rc: *mut c_int) -> c_int;
     pub fn whisper_b200_last_error() -> *const c_char;
+
+    // ---- audio.rs entry points (include/whisper_b200.h: silence chunker, resampler, capture buffer)
+    pub fn nobs_find_silence_boundaries(audio: *const c_float, n_samples: size_t, sample_rate: u32, boundaries: *mut size_t, cap: size_t,
+                                        n_found: *mut size_t) -> c_int;
+    pub fn nobs_split_at_silences_with_overlap(n_samples: size_t, boundaries: *const size_t, n_boundaries: size_t, sample_rate: u32,
+                                               ranges: *mut size_t, n_chunks: *mut size_t) -> c_int;
+    pub fn nobs_split_at_silences(n_samples: size_t, boundaries: *const size_t, n_boundaries: size_t, ranges: *mut size_t, n_chunks: *mut size_t) -> c_int;
+    pub fn nobs_resample_audio(audio: *const c_float, n: size_t, from_rate: u32, to_rate: u32, out: *mut c_float, cap: size_t, n_out: *mut size_t) -> c_int;
+    pub fn nobs_resample_chunk(audio: *const c_float, n: size_t, input_sample_rate: u32, out: *mut c_float, cap: size_t, n_out: *mut size_t) -> c_int;
+    pub fn nobs_mix_to_mono(interleaved: *const c_float, n_frames: size_t, channels: u32, out: *mut c_float) -> c_int;
+    pub fn nobs_calculate_rms(samples: *const c_float, n: size_t) -> c_float;
+    pub fn nobs_audio_buffer_new(sample_rate: u32) -> *mut nobs_audio_buffer;
+    pub fn nobs_audio_buffer_free(b: *mut nobs_audio_buffer);
+    pub fn nobs_audio_buffer_push_samples(b: *mut nobs_audio_buffer, samples: *const c_float, n: size_t);
+    pub fn nobs_audio_buffer_has_silence_boundary(b: *const nobs_audio_buffer) -> c_int;
+    pub fn nobs_audio_buffer_take_chunk_at_silence(b: *mut nobs_audio_buffer, n: *mut size_t) -> *const c_float;
+    pub fn nobs_audio_buffer_take_forced_chunk(b: *mut nobs_audio_buffer, n: *mut size_t) -> *const c_float;
+    pub fn nobs_audio_buffer_take(b: *mut nobs_audio_buffer, n: *mut size_t) -> *const c_float;
+    pub fn nobs_audio_buffer_len(b: *const nobs_audio_buffer) -> size_t;
+    pub fn nobs_audio_buffer_noise_floor(b: *const nobs_audio_buffer) -> c_float;
+}
+
+#[repr(C)]
+pub struct nobs_audio_buffer {
+    _private: [u8; 0],
 }

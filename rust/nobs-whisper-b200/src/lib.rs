@@ -182,3 +182,97 @@ pub fn full_batch(ctx: &WhisperContext, states: &mut [WhisperState], params: Ful
     let r = unsafe { sys::whisper_b200_full_batch(ctx.ctx.0, st.as_ptr(), st.len() as c_int, params.fp, ptrs.as_ptr(), ns.as_ptr(), rc.as_mut_ptr()) };
     if r != 0 { Err(WhisperError::GenericError(r)) } else { Ok(rc) }
 }
+
+/// Drop-in bodies for the reference's `src-tauri/src/audio.rs` functions (same names and signatures), backed by the
+/// library: the window-RMS scan and the resampler run on the GPU, the capture buffer is host logic in the library.
+pub mod audio {
+    use super::sys;
+    use libc::size_t;
+
+    pub const WHISPER_SAMPLE_RATE: u32 = 16000;
+
+    /// audio.rs:400-463
+    pub fn find_silence_boundaries(audio: &[f32], sample_rate: u32) -> Vec<usize> {
+        let mut out = vec![0usize; audio.len() / sample_rate.max(1) as usize + 2];
+        let mut n: size_t = 0;
+        let rc = unsafe { sys::nobs_find_silence_boundaries(audio.as_ptr(), audio.len(), sample_rate, out.as_mut_ptr(), out.len(), &mut n) };
+        assert_eq!(rc, 0, "find_silence_boundaries failed");
+        out.truncate(n.min(out.len()));
+        out
+    }
+
+    /// audio.rs:473-507
+    pub fn split_at_silences_with_overlap(audio: &[f32], boundaries: &[usize], sample_rate: u32) -> Vec<Vec<f32>> {
+        let mut ranges = vec![0usize; 2 * (boundaries.len() + 1)];
+        let mut n: size_t = 0;
+        let rc = unsafe {
+            sys::nobs_split_at_silences_with_overlap(audio.len(), boundaries.as_ptr(), boundaries.len(), sample_rate, ranges.as_mut_ptr(), &mut n)
+        };
+        assert_eq!(rc, 0, "split_at_silences failed");
+        (0..n).map(|k| audio[ranges[2 * k]..ranges[2 * k + 1]].to_vec()).collect()
+    }
+
+    /// audio.rs:467-469
+    pub fn split_at_silences(audio: &[f32], boundaries: &[usize]) -> Vec<Vec<f32>> {
+        split_at_silences_with_overlap(audio, boundaries, WHISPER_SAMPLE_RATE)
+    }
+
+    /// audio.rs:509-563 (`AudioError::ResampleError` on failure)
+    pub fn resample_audio(audio: &[f32], from_rate: u32, to_rate: u32) -> Result<Vec<f32>, String> {
+        let mut n: size_t = 0;
+        let rc = unsafe { sys::nobs_resample_audio(audio.as_ptr(), audio.len(), from_rate, to_rate, std::ptr::null_mut(), 0, &mut n) };
+        if rc != 0 {
+            return Err(format!("resampler error {rc}"));
+        }
+        let mut out = vec![0f32; n];
+        if n > 0 {
+            let rc = unsafe { sys::nobs_resample_audio(audio.as_ptr(), audio.len(), from_rate, to_rate, out.as_mut_ptr(), out.len(), &mut n) };
+            if rc != 0 {
+                return Err(format!("resampler error {rc}"));
+            }
+        }
+        Ok(out)
+    }
+
+    /// audio.rs:329-334
+    pub fn resample_chunk(audio: &[f32], input_sample_rate: u32) -> Result<Vec<f32>, String> {
+        if input_sample_rate == WHISPER_SAMPLE_RATE {
+            return Ok(audio.to_vec());
+        }
+        resample_audio(audio, input_sample_rate, WHISPER_SAMPLE_RATE)
+    }
+
+    /// audio.rs:29-244
+    pub struct AudioBuffer(*mut sys::nobs_audio_buffer);
+    unsafe impl Send for AudioBuffer {}
+    impl AudioBuffer {
+        pub fn new() -> Self { Self::with_sample_rate(48000) }
+        pub fn with_sample_rate(sample_rate: u32) -> Self { AudioBuffer(unsafe { sys::nobs_audio_buffer_new(sample_rate) }) }
+        pub fn push_samples(&mut self, samples: &[f32]) { unsafe { sys::nobs_audio_buffer_push_samples(self.0, samples.as_ptr(), samples.len()) } }
+        pub fn has_silence_boundary(&self) -> bool { unsafe { sys::nobs_audio_buffer_has_silence_boundary(self.0) != 0 } }
+        fn copy_out(p: *const f32, n: size_t) -> Option<Vec<f32>> {
+            if p.is_null() { None } else { Some(unsafe { std::slice::from_raw_parts(p, n) }.to_vec()) }
+        }
+        pub fn take_chunk_at_silence(&mut self) -> Option<Vec<f32>> {
+            let mut n: size_t = 0;
+            let p = unsafe { sys::nobs_audio_buffer_take_chunk_at_silence(self.0, &mut n) };
+            Self::copy_out(p, n)
+        }
+        pub fn take_forced_chunk(&mut self) -> Option<Vec<f32>> {
+            let mut n: size_t = 0;
+            let p = unsafe { sys::nobs_audio_buffer_take_forced_chunk(self.0, &mut n) };
+            Self::copy_out(p, n)
+        }
+        pub fn take(&mut self) -> Vec<f32> {
+            let mut n: size_t = 0;
+            let p = unsafe { sys::nobs_audio_buffer_take(self.0, &mut n) };
+            Self::copy_out(p, n).unwrap_or_default()
+        }
+        pub fn len(&self) -> usize { unsafe { sys::nobs_audio_buffer_len(self.0) } }
+        pub fn is_empty(&self) -> bool { self.len() == 0 }
+        pub fn get_noise_floor(&self) -> f32 { unsafe { sys::nobs_audio_buffer_noise_floor(self.0) } }
+    }
+    impl Drop for AudioBuffer {
+        fn drop(&mut self) { unsafe { sys::nobs_audio_buffer_free(self.0) } }
+    }
+}
