@@ -187,7 +187,8 @@ pub fn full_batch(ctx: &WhisperContext, states: &mut [WhisperState], params: Ful
 /// library: the window-RMS scan and the resampler run on the GPU, the capture buffer is host logic in the library.
 pub mod audio {
     use super::sys;
-    use libc::size_t;
+    #[allow(non_camel_case_types)]
+    type size_t = usize;   // libc::size_t on every LP64 target
 
     pub const WHISPER_SAMPLE_RATE: u32 = 16000;
 
