@@ -85,6 +85,7 @@ bool AudioBuffer::take_forced_chunk(std::vector<float>& out) {
     const size_t max_samples = (size_t)sample_rate_ * kMaxBufferDurationS;
     if (samples_.size() <= max_samples) return false;
     const size_t search = (size_t)sample_rate_ * 5, w = sample_rate_ / 50;
+    if (w == 0) return false;
     const size_t search_start = samples_.size() > search ? samples_.size() - search : 0;
     size_t quietest_pos = search_start;
     float quietest = FLT_MAX;

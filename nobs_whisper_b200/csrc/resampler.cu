@@ -75,6 +75,12 @@ bool build_plan(uint32_t from, uint32_t to, Plan& pl) {
     const size_t a = from / g, b = to / g;
     const size_t chunks = (size_t)std::ceil((float)(1024 / 2) / (float)b);
     const size_t n_in = chunks * a, n_out = chunks * b;
+    // rate pairs with a tiny common divisor (44101 -> 16000) would need gigabyte tables; capture devices use the standard
+    // rates (8 / 11.025 / 16 / 22.05 / 32 / 44.1 / 48 / 88.2 / 96 / 192 kHz), for which the block matrix stays below 40 MB
+    if (2.0 * (double)n_out * (double)n_in > 4.0e7 || 2.0 * (double)a * (double)b * (double)chunks > 6.4e7) {
+        set_last_error("resampler: unsupported rate pair " + std::to_string(from) + " -> " + std::to_string(to));
+        return false;
+    }
     const double cutoff = (double)std::pow(0.4f, 16.0f / (float)n_in) * (n_in > n_out ? (double)n_out / (double)n_in : 1.0);
     std::vector<double> h(n_in);
     double sum = 0.0;
