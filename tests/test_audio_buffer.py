@@ -69,3 +69,27 @@ def test_streaming_session_matches_the_oracle(seed, sr, push):
     assert np.array_equal(got.take(), want.take())
     assert len(got) == 0 and got.overlap_len == 0
     got.close()
+
+
+def test_split_at_silences_host_function_matches_the_oracle():
+    """audio.rs:467-507 through the C ABI (index arithmetic only: no GPU involved)."""
+    from nobs_whisper_b200 import audio
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(SR * 9).astype(np.float32)
+    cases = [[], [SR * 2, SR * 4], [100, SR * 3, SR * 3, SR * 8], [0, SR * 9, SR * 20], [SR * 5, SR * 2]]
+    for b in cases:
+        for sr in (16000, 48000):
+            got = audio.split_at_silences_with_overlap(x, b, sr)
+            want = ao.split_at_silences_with_overlap(x, b, sr)
+            assert len(got) == len(want) and all(np.array_equal(g, w) for g, w in zip(got, want)), (b, sr)
+    # the reference's own case (audio.rs:663-683)
+    six = (np.sin(np.arange(SR * 6, dtype=np.float32) * np.float32(0.001)) * np.float32(0.1)).astype(np.float32)
+    assert [len(c) for c in audio.split_at_silences(six, [SR * 2, SR * 4])] == [SR * 2, SR * 2 + 3200, SR * 2 + 3200]
+
+
+def test_mix_to_mono_host_function():
+    """state.rs:590-594."""
+    from nobs_whisper_b200 import audio
+    st = np.random.default_rng(2).standard_normal(3001).astype(np.float32)
+    for ch in (1, 2, 3):
+        assert np.array_equal(audio.mix_to_mono(st, ch), ao.mix_to_mono(st, ch))
