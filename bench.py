@@ -320,7 +320,12 @@ def main():
         roofline = {
             "bound": "hbm", "kernel": "dec_cross_attention_tc_kernel (decoder cross-attention: TMA ring -> tcgen05 over the head-major cross-KV panels)",
             "achieved": cross_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cross_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
-            "traffic": None, "peak_source": peaks["source"] + " hbm_gbs", "launches": agg_dev["cross_n"],
+            # DRAM bytes per launch: ncu --set full of this kernel (profiles/r1_ncu_full_dec_cross_attention_tc.csv, 8 rows per
+            # launch) read 63.0-63.7 MB + wrote 1.8-3.7 MB against 61.4 MB algorithmic (the 12th TMA box of a panel covers 36 pad
+            # rows; the writes are the attention output and the query tiles); scaled by that ratio to this run's launch size
+            "traffic": 1.06 * agg_dev["cross_bytes"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum at 8 rows per launch (x1.06 of algorithmic), scaled to this launch size",
+            "peak_source": peaks["source"] + " hbm_gbs", "launches": agg_dev["cross_n"],
             "algorithmic_bytes_per_launch": agg_dev["cross_bytes"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
             "avg_launch_us": 1e3 * agg_dev["cross_ms"] / agg_dev["cross_n"] if agg_dev["cross_n"] else None,
             # every 8th layer's launch is timed (engine.cu kCrossSample): extrapolated share of the decode lanes' stream time
