@@ -97,3 +97,24 @@ def test_bf16_engine_on_a_q5_0_model(model_dir):
     o.mel(pcm)
     assert rel_err(st.encoder_output(), o.encode(0)) < 2e-2
     st.close(); ctx.close(); o.close()
+
+
+def test_loader_accepts_quantised_files_and_rejects_damaged_ones(model_dir, tmp_path):
+    """The product's ggml reader without a GPU (host-only handle): every block format parses; truncated block data,
+    an unknown tensor type and an unknown file type are load errors (-> InitError, whisper.rs:41-45)."""
+    import struct
+
+    import nobs_whisper_b200 as nw
+    for name, ft in FTYPES.items():
+        p = ggml_synth.ensure_model(model_dir, "micro", ftype=ft, init="fanin")
+        ctx = nw.WhisperContext(p, host_only=True)
+        assert ctx.n_vocab() == 51865
+        ctx.close()
+    good = open(ggml_synth.ensure_model(model_dir, "micro", ftype=8, init="fanin"), "rb").read()
+    (tmp_path / "cut.bin").write_bytes(good[: len(good) - 777])
+    with pytest.raises(nw.WhisperError):
+        nw.WhisperContext(str(tmp_path / "cut.bin"), host_only=True)
+    bad_ftype = good[:4] + struct.pack("<11i", *struct.unpack("<11i", good[4:48])[:10], 5) + good[48:]
+    (tmp_path / "ftype.bin").write_bytes(bad_ftype)
+    with pytest.raises(nw.WhisperError):
+        nw.WhisperContext(str(tmp_path / "ftype.bin"), host_only=True)
