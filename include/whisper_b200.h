@@ -296,6 +296,13 @@ struct whisper_context* whisper_b200_init_host_only(const char* path_model);
 int whisper_b200_full_batch(struct whisper_context* ctx, struct whisper_state* const* states, int n, struct whisper_full_params params,
                             const float* const* samples, const int* n_samples, int* rc);
 
+/* Batched whisper_decode_with_state: ONE decoder round over n states (each already encoded: whisper_encode_with_state).
+ * State i contributes n_tokens[i] token rows (tokens are concatenated in `tokens`) at positions n_past[i].. ; the logits of its
+ * last row are written to logits_out[i * n_vocab .. ] (fp32).  All rows run in the same launches (the decode-lane path `full`
+ * uses, on lane `lane`), so this is the stage-level hook for teacher-forced parity checks of step batches.  0 on success. */
+int whisper_b200_decode_batch(struct whisper_context* ctx, struct whisper_state* const* states, int n, const whisper_token* tokens,
+                              const int* n_tokens, const int* n_past, int lane, float* logits_out);
+
 /* Copy of the normalised log-mel of the last pcm_to_mel/full call, upstream layout
  * [n_mel][n_len]; returns n_len (or the needed float count negated if cap is too small). */
 int whisper_b200_get_mel(struct whisper_state* state, float* out, size_t cap_floats);

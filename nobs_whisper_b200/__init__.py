@@ -6,5 +6,5 @@ ctypes layers over the C ABI of libnobswhisper_b200.so (include/whisper_b200.h);
 runs in that library's sm_100a kernels.
 """
 from .api import (FullParams, SamplingStrategy, WhisperContext, WhisperContextParameters, WhisperError, WhisperSegment,  # noqa: F401
-                  WhisperState, full_batch)
+                  WhisperState, decode_batch, full_batch)
 from .engine import NoModel, LoadError, TranscriptionError, WhisperEngine, filter_hallucinations  # noqa: F401

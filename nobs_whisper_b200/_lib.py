@@ -181,6 +181,7 @@ SIGNATURES = {
     "whisper_b200_precision": (C.c_int, [vp]),
     "whisper_b200_decode_lanes": (C.c_int, [vp]),
     "whisper_b200_init_host_only": (vp, [C.c_char_p]),
+    "whisper_b200_decode_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int32), ip, ip, C.c_int, fp]),
     "whisper_b200_full_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, WhisperFullParams, C.POINTER(fp), ip, ip]),
     "whisper_b200_get_mel": (C.c_int, [vp, fp, C.c_size_t]),
     "whisper_b200_get_encoder_output": (C.c_int, [vp, vp, fp, C.c_size_t]),

@@ -325,6 +325,23 @@ class WhisperState:
         return out
 
 
+def decode_batch(ctx: WhisperContext, states: list[WhisperState], tokens: list, n_past: list[int], lane: int = 0) -> np.ndarray:
+    """B200 extension: one decoder round over several encoded states (whisper_b200_decode_batch); tokens[i] are the rows
+    state i contributes at positions n_past[i]..; returns the last-row logits [len(states)][n_vocab]."""
+    L = _lib.lib()
+    n = len(states)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32).ravel() for t in tokens]), dtype=np.int32)
+    nt = np.ascontiguousarray([len(t) for t in tokens], dtype=np.int32)
+    npast = np.ascontiguousarray(n_past, dtype=np.int32)
+    handles = (C.c_void_p * n)(*[s._h for s in states])
+    out = np.zeros((n, ctx.n_vocab()), np.float32)
+    rc = L.whisper_b200_decode_batch(ctx._h, handles, n, flat.ctypes.data_as(C.POINTER(C.c_int32)), nt.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     npast.ctypes.data_as(C.POINTER(C.c_int32)), int(lane), _fptr(out))
+    if rc != 0:
+        raise WhisperError("FailedToDecode: " + (L.whisper_b200_last_error() or b"").decode(errors="replace"))
+    return out
+
+
 def full_batch(ctx: WhisperContext, states: list[WhisperState], params: FullParams, audios: list) -> list[int]:
     """B200 extension: `full` over independent audios in lock step (whisper_b200_full_batch)."""
     L = _lib.lib()

@@ -6,6 +6,8 @@
 #include <mutex>
 #include <thread>
 
+#include <memory>
+
 #include "state.h"
 
 namespace nobs {
@@ -48,38 +50,55 @@ struct whisper_context_params whisper_context_default_params(void) {
     return p;
 }
 
+// No exception may cross the C ABI (the callers are Rust / ctypes): every entry point that can allocate or parse
+// reports failure through its return value and whisper_b200_last_error().
 struct whisper_context* whisper_b200_init_from_file(const char* path_model, struct whisper_context_params params, int precision) {
     if (!path_model) { set_last_error("null model path"); return nullptr; }
-    auto* ctx = new whisper_context();
-    ctx->params = params;
-    std::string err;
-    if (!load_ggml_model(path_model, ctx->model, err)) {
-        set_last_error("failed to load model: " + err);
-        delete ctx;
+    std::unique_ptr<whisper_context> ctx;
+    try {
+        ctx.reset(new whisper_context());
+        ctx->params = params;
+        std::string err;
+        if (!load_ggml_model(path_model, ctx->model, err)) {
+            set_last_error("failed to load model: " + err);
+            return nullptr;
+        }
+        ctx->engine.reset(Engine::create(ctx->model, params.gpu_device, resolve_precision(precision), err));
+        if (!ctx->engine) {
+            set_last_error("failed to initialise the GPU engine: " + err);
+            return nullptr;
+        }
+        ctx->model.tensors.clear();  // weights now live in HBM
+    } catch (const std::exception& e) {
+        set_last_error(std::string("failed to load model: ") + e.what());
+        return nullptr;
+    } catch (...) {
+        set_last_error("failed to load model: unknown exception");
         return nullptr;
     }
-    ctx->engine.reset(Engine::create(ctx->model, params.gpu_device, resolve_precision(precision), err));
-    if (!ctx->engine) {
-        set_last_error("failed to initialise the GPU engine: " + err);
-        delete ctx;
-        return nullptr;
-    }
-    ctx->model.tensors.clear();  // weights now live in HBM
-    return ctx;
+    return ctx.release();
 }
 
 struct whisper_context* whisper_b200_init_host_only(const char* path_model) {
     if (!path_model) { set_last_error("null model path"); return nullptr; }
-    auto* ctx = new whisper_context();
-    ctx->params = whisper_context_default_params();
-    std::string err;
-    if (!load_ggml_model(path_model, ctx->model, err)) {
-        set_last_error("failed to load model: " + err);
-        delete ctx;
+    std::unique_ptr<whisper_context> ctx;
+    try {
+        ctx.reset(new whisper_context());
+        ctx->params = whisper_context_default_params();
+        std::string err;
+        if (!load_ggml_model(path_model, ctx->model, err)) {
+            set_last_error("failed to load model: " + err);
+            return nullptr;
+        }
+        ctx->model.tensors.clear();
+    } catch (const std::exception& e) {
+        set_last_error(std::string("failed to load model: ") + e.what());
+        return nullptr;
+    } catch (...) {
+        set_last_error("failed to load model: unknown exception");
         return nullptr;
     }
-    ctx->model.tensors.clear();
-    return ctx;  // no engine: every compute entry point fails on this handle
+    return ctx.release();  // no engine: every compute entry point fails on this handle
 }
 
 struct whisper_context* whisper_init_from_file_with_params_no_state(const char* path_model, struct whisper_context_params params) {
@@ -179,7 +198,15 @@ int whisper_b200_full_batch(struct whisper_context* ctx, struct whisper_state* c
         if (!states[i] || states[i]->ctx != ctx || (n_samples[i] > 0 && !samples[i])) { set_last_error("bad state/audio in batch"); return -100; }
         for (int k = 0; k < i; ++k) if (states[k] == states[i]) { set_last_error("a state appears twice in the batch"); return -100; }
     }
-    return full_batch(ctx, states, n, params, samples, n_samples, rc);
+    try {
+        return full_batch(ctx, states, n, params, samples, n_samples, rc);
+    } catch (const std::exception& e) {
+        set_last_error(std::string("full: ") + e.what());
+    } catch (...) {
+        set_last_error("full: unknown exception");
+    }
+    for (int i = 0; i < n; ++i) rc[i] = -100;
+    return -100;
 }
 
 int whisper_full_with_state(struct whisper_context* ctx, struct whisper_state* state, struct whisper_full_params params,
@@ -248,10 +275,15 @@ whisper_token whisper_token_transcribe(struct whisper_context* c) { return c->mo
 
 int whisper_tokenize(struct whisper_context* c, const char* text, whisper_token* tokens, int n_max_tokens) {
     if (!c || !text) return 0;
-    const auto res = tokenize(c->model.vocab, text);
-    if (n_max_tokens < (int)res.size()) return -(int)res.size();
-    for (size_t i = 0; i < res.size(); ++i) tokens[i] = res[i];
-    return (int)res.size();
+    try {
+        const auto res = tokenize(c->model.vocab, text);
+        if (n_max_tokens < (int)res.size()) return -(int)res.size();
+        for (size_t i = 0; i < res.size(); ++i) tokens[i] = res[i];
+        return (int)res.size();
+    } catch (...) {
+        set_last_error("tokenize: out of memory");
+        return 0;
+    }
 }
 int whisper_token_count(struct whisper_context* c, const char* text) { return -whisper_tokenize(c, text, nullptr, 0); }
 int whisper_lang_max_id(void) { return kNumLangs - 1; }
@@ -298,6 +330,36 @@ int whisper_decode_with_state(struct whisper_context* ctx, struct whisper_state*
     std::vector<SampleResult> res;
     st->logits.resize(ctx->model.hp.n_vocab);
     if (!e.decode(rows, samp, sps, res, st->logits.data())) { set_last_error(e.last_error()); return -1; }
+    return 0;
+}
+int whisper_b200_decode_batch(struct whisper_context* ctx, struct whisper_state* const* states, int n, const whisper_token* tokens, const int* n_tokens,
+                              const int* n_past, int lane, float* logits_out) {
+    if (!ctx || !ctx->engine || !states || !tokens || !n_tokens || !n_past || !logits_out || n <= 0) { set_last_error("decode_batch: bad arguments"); return -1; }
+    Engine& e = *ctx->engine;
+    if (lane < 0 || lane >= e.n_lanes()) { set_last_error("decode_batch: no such lane"); return -1; }
+    try {
+        std::lock_guard<std::mutex> lock(e.mu);
+        std::vector<RowDesc> rows;
+        std::vector<int> samp;
+        std::vector<SampleParams> sps;
+        const whisper_token* t = tokens;
+        for (int i = 0; i < n; ++i) {
+            whisper_state* st = states[i];
+            if (!st || st->ctx != ctx || st->audio_slot < 0 || n_tokens[i] <= 0 || n_past[i] < 0) { set_last_error("decode_batch: bad state / token count"); return -1; }
+            if (!ensure_state_slots(ctx, st, 1)) return -1;
+            for (int k = 0; k < n_tokens[i]; ++k) rows.push_back(RowDesc{t[k], n_past[i] + k, st->kv_slots[0], st->audio_slot});
+            t += n_tokens[i];
+            samp.push_back((int)rows.size() - 1);
+            SampleParams sp{};
+            sp.ts_initial_limit = ctx->model.hp.n_vocab;
+            sps.push_back(sp);
+        }
+        std::vector<SampleResult> res;
+        if (!e.decode_submit(lane, rows, samp, sps, logits_out) || !e.decode_collect(lane, res)) { set_last_error(e.last_error()); return -1; }
+    } catch (const std::exception& ex) {
+        set_last_error(std::string("decode_batch: ") + ex.what());
+        return -1;
+    }
     return 0;
 }
 float* whisper_get_logits_from_state(struct whisper_state* st) { return st && !st->logits.empty() ? st->logits.data() : nullptr; }

@@ -101,7 +101,7 @@ public:
             cudaMemcpy(h.data(), trace_buf_ + 4 + 4 * skip, h.size() * 8, cudaMemcpyDeviceToHost);
             if (FILE* f = fopen(trace_path_.c_str(), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
             fprintf(stderr, "[nobs trace] %llu entries recorded, wrote %llu from %llu to %s\n", n, cnt, skip, trace_path_.c_str());
-            trace_set_kernels(nullptr, 0); trace_set_gemm(nullptr, 0); trace_set_cross(nullptr, 0);
+            trace_set_kernels(nullptr, 0); trace_set_gemm(nullptr, 0); trace_set_cross(nullptr, 0); trace_set_chain(nullptr, 0);
             cudaFree(trace_buf_);
         }
         for (auto& e : main_marks_.pool) cudaEventDestroy(e);
@@ -141,6 +141,7 @@ public:
             trace_set_kernels(trace_buf_, trace_cap_);
             trace_set_gemm(trace_buf_, trace_cap_);
             trace_set_cross(trace_buf_, trace_cap_);
+            trace_set_chain(trace_buf_, trace_cap_);
         }
         CUDA_OK(cudaStreamSynchronize(stream_));
         return true;
@@ -359,6 +360,7 @@ public:
         float* logits = nullptr;
         float* probs = nullptr;           // [S][n_vocab] filtered probabilities of the last round (K6 scratch)
         float* partial = nullptr;
+        unsigned int* bar = nullptr;      // device-wide barrier state of the fused projection chains (count, generation)
         int* sched = nullptr;             // 2 x (work, exit) counters of the streaming cross-attention kernel: consecutive
         unsigned cross_seq = 0;           // launches alternate, a launch may start its prologue while the previous one drains
         char* pin = nullptr; size_t pin_cap = 0;
@@ -369,6 +371,7 @@ public:
         int pend_S = 0; size_t pend_off = 0; size_t pend_pin_off = 0;
         std::vector<SampleResult> results;
         int last_logit_rows = 0;
+        size_t last_logit_base = 0;       // lane-wide index of the first sample whose logits the lane still holds (last chunk only)
         std::chrono::steady_clock::time_point t_submit;
     };
     int n_lanes() const override { return (int)lanes_.size(); }
@@ -408,7 +411,15 @@ public:
             size_t r1 = std::min(rows.size(), r0 + (size_t)dec_rows_);
             size_t sj = si;
             while (sj < sample_rows.size() && (size_t)sample_rows[sj] < r1) {
-                if (sj - si == (size_t)dec_samples_) { r1 = (size_t)sample_rows[sj]; break; }
+                if (sj - si == (size_t)dec_samples_) {
+                    // the sample budget ends inside this chunk: cut in front of the row sample sj refers to.  Several samples
+                    // may share that row (prefill with best_of / beam_size > 1 samples the prompt's last row n_cur times):
+                    // all of them move to the next chunk, so every sample of a chunk indexes a row inside [r0, r1).
+                    const size_t row = (size_t)sample_rows[sj];
+                    while (sj > si && (size_t)sample_rows[sj - 1] == row) --sj;
+                    r1 = row;
+                    break;
+                }
                 ++sj;
             }
             if (r1 == r0) { err_ = "decode: cannot make progress"; L.inflight = false; return false; }
@@ -552,6 +563,107 @@ public:
         return true;
     }
 
+    // The same layers with the projection chains fused (decode_chain_sm100.cu): per layer 4 launches instead of 12 —
+    // [out-proj + LN + cross-query] -> cross-attention -> [cross-out + LN + FC1 + GELU + FC2 + LN + next QKV] -> self-attention.
+    // Arithmetic and split order are those of decode_layers_skinny: results are bit-identical.
+    bool decode_layers_chain(Lane& Ln, const RowDesc* drows, int R, bool distinct_slots) {
+        const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        cudaStream_t st = Ln.stream;
+        const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
+        const size_t self_slot = (size_t)Ld * 2 * self_kv;
+        const size_t cross_kv = (size_t)kWinRows * d;
+        const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
+        const bool fuse_qkv = fuse_qkv_ && distinct_slots;
+        const bf16* y = reinterpret_cast<const bf16*>(Ln.y);
+        const bf16* att = reinterpret_cast<const bf16*>(Ln.att);
+        const bf16* h = reinterpret_cast<const bf16*>(Ln.h);
+        struct Chain {
+            ChainDesc cd;
+            const bf16* W[kChainMaxSteps];
+            const bf16* X[kChainMaxSteps];
+            int ldx[kChainMaxSteps];
+            int n = 0;
+        };
+        auto add = [&](Chain& c, const bf16* X, int K, const T* W, int N) -> SkinnyEpilogue& {
+            ChainStep& s = c.cd.step[c.n];
+            s = ChainStep();
+            s.N = N; s.K = K; s.reduce = 1;
+            c.W[c.n] = reinterpret_cast<const bf16*>(W); c.X[c.n] = X; c.ldx[c.n] = K;
+            return c.cd.step[c.n++].e;
+        };
+        auto run = [&](Chain& c) -> bool {
+            c.cd.n_steps = c.n; c.cd.R = R; c.cd.partial = Ln.partial; c.cd.bar = Ln.bar;
+            mark_begin(Ln.tm, detail_);
+            if (!launch_dec_chain_sm100(c.cd, c.W, c.X, c.ldx, chain_stages_, st)) return gemm_fail();
+            mark_end(Ln.tm, detail_, 10);
+            return true;
+        };
+        // QKV projection of layer l as the last step of a chain: either left as partial sums for the self-attention
+        // kernel (one row per KV slot) or reduced here with the KV-cache append
+        auto add_qkv = [&](Chain& c, int l) {
+            const Layer<T>& L = dec_[l];
+            SkinnyEpilogue& e = add(c, y, d, L.wqkv, 3 * d);
+            if (fuse_qkv) { c.cd.step[c.n - 1].reduce = 0; return; }
+            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+            e.bias = L.bqkv; e.out = Ln.qkv; e.out_ld = 3 * d;
+            e.rows = drows; e.kpanel = kc; e.vpanel = kc + self_kv; e.slot_stride = self_slot; e.n_pos_cap = ntc; e.d = d;
+        };
+        launch_layernorm<T>(Ln.x, d, dec_[0].ln1_g, dec_[0].ln1_b, Ln.y, d, R, d, st);
+        {
+            Chain c;
+            add_qkv(c, 0);
+            if (!run(c)) return false;
+        }
+        for (int l = 0; l < Ld; ++l) {
+            const Layer<T>& L = dec_[l];
+            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+            T* vc = kc + self_kv;
+            mark_begin(Ln.tm, detail_);
+            if (fuse_qkv) {
+                QkvPartials qp;
+                qp.partial = Ln.partial; qp.splits = skinny_gemm_splits(3 * d, d); qp.plane = (size_t)R * 3 * d; qp.ld = 3 * d; qp.bias = L.bqkv;
+                launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st, &qp);
+            } else {
+                launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
+            }
+            mark_end(Ln.tm, detail_, 12);
+            {   // out projection + residual + cross-attention LayerNorm, then the cross-attention query (left as partial sums)
+                Chain c;
+                SkinnyEpilogue& e = add(c, att, d, L.wo, d);
+                e.bias = L.bo; e.x = Ln.x; e.ln_g = L.lnc_g; e.ln_b = L.lnc_b; e.y = Ln.y;
+                add(c, y, d, L.wcq, d);
+                c.cd.step[c.n - 1].reduce = 0;
+                if (!run(c)) return false;
+            }
+            const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
+            const T* cv = ck + cross_kv;
+            const bool timed = profiling && (l % kCrossSample) == 0;
+            CrossQPartials qp;
+            qp.partial = Ln.partial; qp.splits = skinny_gemm_splits(d, d); qp.plane = (size_t)R * d; qp.ld = d; qp.bias = L.bcq;
+            mark_begin(Ln.tm, timed || detail_);
+            if (!launch_dec_cross_attention_tc_sm100(drows, R, nullptr, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
+                                                     (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
+                                                     cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
+                return gemm_fail();
+            if (timed) { mark_end(Ln.tm, true, 2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            {   // cross out-projection + residual + MLP LayerNorm, FC1 + GELU, FC2 + residual + next LayerNorm, next layer's QKV
+                Chain c;
+                SkinnyEpilogue& e1 = add(c, att, d, L.wco, d);
+                e1.bias = L.bco; e1.x = Ln.x; e1.ln_g = L.ln2_g; e1.ln_b = L.ln2_b; e1.y = Ln.y;
+                SkinnyEpilogue& e2 = add(c, y, d, L.w1, 4 * d);
+                e2.bias = L.b1; e2.act = 1; e2.out = Ln.h; e2.out_ld = 4 * d;
+                SkinnyEpilogue& e3 = add(c, h, 4 * d, L.w2, d);
+                e3.bias = L.b2; e3.x = Ln.x;
+                if (l + 1 < Ld) {
+                    e3.ln_g = dec_[l + 1].ln1_g; e3.ln_b = dec_[l + 1].ln1_b; e3.y = Ln.y;
+                    add_qkv(c, l + 1);
+                }
+                if (!run(c)) return false;
+            }
+        }
+        return true;
+    }
+
     // logits = ys * tok_emb^T.  For a step batch (S <= 128 sample rows, bf16) this is the same weight-streaming shape as
     // the layer projections: the swap-AB kernel with one K split writes fp32 [S][n_vocab] directly (406 weight tiles
     // over all SMs) instead of two ragged waves of 128 x 256 tiles.
@@ -634,7 +746,8 @@ public:
                 std::sort(slots.begin(), slots.end());
                 distinct = std::adjacent_find(slots.begin(), slots.end()) == slots.end();
             }
-            if (!decode_layers_skinny(Ln, drows, R, distinct)) return false;
+            const bool chain = use_chain_ && cross_mode_ == 2 && fuse_cross_q_;
+            if (!(chain ? decode_layers_chain(Ln, drows, R, distinct) : decode_layers_skinny(Ln, drows, R, distinct))) return false;
         } else {
             for (int l = 0; l < Ld; ++l) {
                 const Layer<T>& L = dec_[l];
@@ -675,6 +788,7 @@ public:
         }
         host_issue_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
         Ln.last_logit_rows = S;
+        Ln.last_logit_base = res_off;
         return true;
     }
 
@@ -682,7 +796,10 @@ public:
         CUDA_OK(cudaSetDevice(device_));
         if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "lang_probs: no such lane"; return false; }
         Lane& L = lanes_[lane];
-        if (L.inflight || sample_index < 0 || sample_index >= L.last_logit_rows) { err_ = "lang_probs: no such logits row"; return false; }
+        // only the last chunk's logits are still in the lane's buffer: index relative to it
+        const long local = (long)sample_index - (long)L.last_logit_base;
+        if (L.inflight || local < 0 || local >= L.last_logit_rows) { err_ = "lang_probs: the logits of that sample row are no longer held by the lane"; return false; }
+        sample_index = (int)local;
         CUDA_OK(cudaStreamSynchronize(L.stream));
         if (!lane_scratch(L, 1024)) return false;
         float* dp = reinterpret_cast<float*>(L.scratch);
@@ -1034,6 +1151,10 @@ private:
         // with several lanes the step GEMMs run a 2-deep ring (49 KB at 64 rows): two of them fit next to the two
         // attention CTAs (2 x 57 KB) an SM holds for another lane
         set_skinny_gemm_stages(env_int("NOBS_WHISPER_SKINNY_STAGES", n_lanes > 1 ? 2 : 3));
+        // fused projection chains need every lane's chain grid co-resident (decode_chain_sm100.cu); otherwise the
+        // multi-launch path runs
+        chain_stages_ = env_int("NOBS_WHISPER_CHAIN_STAGES", chain_stages_for_lanes(n_lanes));
+        use_chain_ = env_int("NOBS_WHISPER_CHAIN", 1) != 0 && !f32 && chain_fits(n_lanes, chain_stages_);
         // The encoder and every decode lane own their activations: a lane may decode while the encoder
         // works on other windows and while other lanes decode.
         auto plan_enc = [&](Arena& a) {
@@ -1055,6 +1176,7 @@ private:
             L.h = (T*)a.take(R * 4 * d * sizeof(T));
             L.partial = (float*)a.take((size_t)16 << 20);  // skinny-GEMM split-K partials: <= 4 splits x 128 rows x 5120 cols (FC1) fp32
             L.sched = (int*)a.take(256);
+            L.bar = (unsigned int*)a.take(256);
             L.ys = (T*)a.take(S * d * sizeof(T));
             L.logits = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
             L.probs = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
@@ -1127,6 +1249,8 @@ private:
     bool use_skinny_ = true;
     int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
     int cross_ctas_ = 0;              // > 0: cap that kernel's grid
+    bool use_chain_ = true;           // step batches: projection chains between the attention kernels as single persistent launches
+    int chain_stages_ = 3;
     bool fuse_qkv_ = true;            // single-token steps: the self-attention kernel finishes the QKV projection's split-K sums
     bool skinny_logits_ = true;       // step batches: logits through the swap-AB weight-streaming GEMM
     bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself

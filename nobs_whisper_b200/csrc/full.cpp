@@ -16,6 +16,9 @@ namespace nobs {
 namespace {
 
 constexpr int kChunk = WHISPER_CHUNK_SIZE;
+// Minimum audio (mel frames, 10 ms each) whisper_full still processes: whisper.cpp v1.7.x `delta_min` = 100 ms.  The reference app
+// hands over every clip longer than 1600 samples (state.rs:749 'at least 0.1 second').
+constexpr int kDeltaMin = 10;
 
 struct Sequence {
     std::vector<whisper_token_data> tokens;
@@ -161,8 +164,8 @@ public:
             for (int ln = 0; ln < n_lanes_; ++ln) {
                 LaneState& L = lanes_[ln];
                 if (L.inflight) {
-                    if (!eng_.decode_collect(ln, L.res)) return fail_all(rc, n, -8);
                     L.inflight = false;
+                    if (!eng_.decode_collect(ln, L.res)) return fail_all(rc, n, -8);
                     for (int i : L.jobs) consume(jobs_[i]);
                     if (!L.kv_pairs_a.empty()) {
                         if (!eng_.kv_copy(ln, L.kv_pairs_a)) return fail_all(rc, n, -8);
@@ -209,7 +212,16 @@ public:
 
 private:
     int fail_all(int* rc, int n, int code) {
-        set_last_error(eng_.last_error());
+        const std::string first_error = eng_.last_error();
+        // other lanes may still have a round in flight: wait for them (results are dropped) so that no kernel writes the
+        // states' KV slots after this call returns and no lane is left "busy" for the next call on the context
+        for (size_t ln = 0; ln < lanes_.size(); ++ln) {
+            if (!lanes_[ln].inflight) continue;
+            std::vector<SampleResult> dropped;
+            eng_.decode_collect((int)ln, dropped);
+            lanes_[ln].inflight = false;
+        }
+        set_last_error(first_error);
         for (int i = 0; i < n; ++i) rc[i] = (jobs_.size() > (size_t)i && jobs_[i].rc != 0) ? jobs_[i].rc : code;
         return code;
     }
@@ -224,7 +236,7 @@ private:
         if (!j.need_lang) j.lang = lang;
         j.seek_start = p.offset_ms / 10;
         j.seek_end = p.duration_ms == 0 ? st->mel.n_len_org : j.seek_start + p.duration_ms / 10;
-        if (st->mel.raw == nullptr || j.seek_end < j.seek_start + 100) {  // under 1 s of audio: nothing to do
+        if (st->mel.raw == nullptr || j.seek_end < j.seek_start + kDeltaMin) {  // under 100 ms of audio: nothing to do
             j.phase = Phase::Finished;
             return 0;
         }
@@ -238,6 +250,26 @@ private:
         if (j.n_decoders > WHISPER_MAX_DECODERS) { j.rc = -4; j.phase = Phase::Finished; return 0; }
         if (p.strategy == WHISPER_SAMPLING_BEAM_SEARCH && p.beam_search.beam_size > kMaxTopK) { j.rc = -4; j.phase = Phase::Finished; return 0; }
         if (p.audio_ctx > hp_.n_audio_ctx) { j.rc = -5; j.phase = Phase::Finished; return 0; }
+        {
+            // Parameters that change the transcript upstream and are not implemented here are refused, never silently ignored
+            // (the reference sets none of them, whisper.rs:88-124).  Observer callbacks (new_segment / progress) do not change
+            // results and stay ignored.
+            const char* what = nullptr;
+            if (p.audio_ctx != 0) what = "audio_ctx != 0";
+            else if (p.vad) what = "vad";
+            else if (p.suppress_nst) what = "suppress_nst";
+            else if (p.suppress_regex && *p.suppress_regex) what = "suppress_regex";
+            else if (p.logits_filter_callback) what = "logits_filter_callback";
+            else if (p.encoder_begin_callback) what = "encoder_begin_callback";
+            else if (p.abort_callback) what = "abort_callback";
+            else if (p.grammar_rules && p.n_grammar_rules > 0) what = "grammar_rules";
+            else if (p.tdrz_enable) what = "tdrz_enable";
+            if (what) {
+                set_last_error(std::string("whisper_full: parameter not supported by this engine: ") + what);
+                j.rc = -100; j.phase = Phase::Finished;
+                return 0;
+            }
+        }
         if (p.no_context) st->prompt_past.clear();
         {
             std::vector<whisper_token> pt;
@@ -277,9 +309,9 @@ private:
         enc_.clear();
         for (int ji : L.jobs) {
             Job& j = jobs_[ji];
-            if (j.phase == Phase::Window && j.seek + 100 >= j.seek_end) j.phase = Phase::Finished;  // under 1 s left
+            if (j.phase == Phase::Window && j.seek + kDeltaMin >= j.seek_end) j.phase = Phase::Finished;  // under 100 ms left
             if (j.phase != Phase::Window && j.phase != Phase::LangDetect) continue;
-            const int seek = j.phase == Phase::LangDetect ? j.seek_start : j.seek;
+            const int seek = j.phase == Phase::LangDetect ? 0 : j.seek;   // whisper_lang_auto_detect_with_state(ctx, state, 0, ...): always offset 0
             if (j.st->encoded_seek != seek) {
                 enc_.push_back(EncodeRequest{&j.st->mel, seek, j.st->audio_slot});
                 j.st->encoded_seek = seek;
@@ -495,9 +527,9 @@ private:
                 d.has_ts = true;
             }
             if (tok.id == vocab_.token_eot || (j.p.max_tokens > 0 && i >= j.p.max_tokens) ||
-                (d.has_ts && j.seek + d.seek_delta + 100 >= j.seek_end)) {
+                (d.has_ts && j.seek + d.seek_delta + kDeltaMin >= j.seek_end)) {
                 if (result_len == 0 && !j.p.no_timestamps) {
-                    if (j.seek + d.seek_delta + 100 >= j.seek_end) result_len = i + 1;
+                    if (j.seek + d.seek_delta + kDeltaMin >= j.seek_end) result_len = i + 1;
                     else { d.failed = true; continue; }
                 }
                 if (j.p.single_segment || j.p.no_timestamps) { result_len = i + 1; d.seek_delta = 100 * kChunk; }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 
 #include "device_utils.cuh"
@@ -386,6 +387,34 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64
 }
 
 namespace {
+struct TmapKey {
+    const void* ptr; uint64_t inner, rows, stride; uint32_t box_inner, box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && rows == o.rows && stride == o.stride && box_inner == o.box_inner && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.inner * 0xC2B2AE3D27D4EB4Full) ^ (k.rows << 17) ^ (k.stride << 29) ^ ((uint64_t)k.box_inner << 41) ^ ((uint64_t)k.box_rows << 52);
+        return (size_t)(h ^ (h >> 31));
+    }
+};
+}  // namespace
+
+bool get_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_inner,
+                      uint32_t box_rows) {
+    thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    const TmapKey key{ptr, inner, rows, row_stride_elems, box_inner, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return true; }
+    if (!make_tmap_bf16_2d(map, ptr, inner, rows, row_stride_elems, box_inner, box_rows)) return false;
+    if (cache.size() > 65536) cache.clear();   // a descriptor is a pure function of its key: dropping the cache is always safe
+    cache.emplace(key, *map);
+    return true;
+}
+
+namespace {
 
 int num_sms() {
     static int n = 0;
@@ -402,8 +431,8 @@ template <int BN, typename TC>
 bool launch_cfg(const bf16* A, int lda, const bf16* W, int ldw, TC* C, int ldc, int M, int N, int K, const Epilogue& e, cudaStream_t s) {
     using cfg = Cfg<BN>;
     CUtensorMap ta, tb;
-    if (!make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return false;
-    if (!make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN)) return false;
+    if (!get_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return false;
+    if (!get_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN)) return false;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES) != cudaSuccess) {
@@ -429,8 +458,8 @@ bool launch_skinny_cfg(const bf16* X, int ldx, const bf16* W, int ldw, float* pa
                        cudaStream_t s) {
     constexpr int SMEM = STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
     CUtensorMap tw, tx;
-    if (!make_tmap_bf16_2d(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BM)) return false;
-    if (!make_tmap_bf16_2d(&tx, X, (uint64_t)K, (uint64_t)R, (uint64_t)ldx, BK, BN)) return false;
+    if (!get_tmap_bf16_2d(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BM)) return false;
+    if (!get_tmap_bf16_2d(&tx, X, (uint64_t)K, (uint64_t)R, (uint64_t)ldx, BK, BN)) return false;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_skinny_sm100_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {

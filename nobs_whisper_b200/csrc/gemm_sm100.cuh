@@ -40,6 +40,29 @@ struct CrossQPartials {
 bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
                                          size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s,
                                          const CrossQPartials* qpart = nullptr);
+// Decoder projection chain (decode_chain_sm100.cu): up to kChainMaxSteps dependent swap-AB split-K projections of one step
+// batch (R <= 128 rows) in ONE persistent launch, separated by device-wide barriers instead of kernel boundaries.  Every
+// step but the last must be reduced (`reduce` = 1: SkinnyEpilogue semantics, identical arithmetic to skinny_reduce_kernel);
+// the last may leave its partial sums in `partial` for the attention kernel that follows.
+constexpr int kChainMaxSteps = 4;
+struct ChainStep {
+    int N = 0, K = 0;                                // out[r][n] = sum_k X[r][k] * W[n][k]
+    int m_tiles = 0, splits = 0, kb_per_split = 0;   // filled by the launcher (same tiling as launch_gemm_skinny_bf16_sm100)
+    int reduce = 0;
+    SkinnyEpilogue e;                                // partial / splits / R / N are filled by the launcher
+};
+struct ChainDesc {
+    int n_steps = 0, R = 0;
+    ChainStep step[kChainMaxSteps];
+    float* partial = nullptr;        // split-K workspace of the lane
+    unsigned int* bar = nullptr;     // 2 zero-initialised words owned by the lane (device-wide barrier state)
+};
+// W[i]: [N_i][K_i] weights, X[i]: [R][ldx[i]] activations of step i.  stages: shared-memory ring depth (2 or 3).
+bool launch_dec_chain_sm100(ChainDesc& cd, const bf16* const* W, const bf16* const* X, const int* ldx, int stages, cudaStream_t s);
+int chain_stages_for_lanes(int n_lanes);
+// true when n_lanes concurrent chain grids can always become co-resident (no mutual wait for SM slots)
+bool chain_fits(int n_lanes, int stages);
+void trace_set_chain(unsigned long long* buf, unsigned int cap);
 const char* sm100_last_error();
 
 }  // namespace nobs

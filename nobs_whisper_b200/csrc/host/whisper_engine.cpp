@@ -235,6 +235,7 @@ WhisperError WhisperEngine::transcribe_recording(const float* audio, size_t n, c
                                                  const std::optional<std::string>& vocabulary, bool parallel, std::string& out) const {
     out.clear();
     if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
+    if (n <= 1600) return WhisperError{WhisperError::None, ""};   // state.rs:749: only audio longer than 0.1 s is transcribed
     std::vector<std::pair<size_t, size_t>> pieces;
     const size_t whisper_max_samples = 30 * 16000;   // state.rs:758
     if (n > whisper_max_samples) {

@@ -1,5 +1,9 @@
 #include "model.h"
 
+#include <cstdint>
+
+#include <algorithm>
+
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -215,6 +219,13 @@ bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
     if (v.token_beg >= hp.n_vocab) { err = "vocabulary too small for timestamp tokens"; return false; }
 
     // tensors until EOF
+    size_t file_size = 0;
+    {
+        const long here = ftell(fp.f);
+        fseek(fp.f, 0, SEEK_END);
+        file_size = (size_t)std::max(0L, ftell(fp.f));
+        fseek(fp.f, here, SEEK_SET);
+    }
     std::vector<uint16_t> half;
     std::vector<uint8_t> raw;
     while (true) {
@@ -232,6 +243,16 @@ bool load_ggml_model(const std::string& path, HostModel& m, std::string& err) {
         }
         std::string name((size_t)name_len, '\0');
         if (!fp.read(&name[0], name_len)) { err = "truncated tensor name"; return false; }
+        // bound the element count against what the file still holds BEFORE allocating: a damaged header must come back as
+        // an error, not as std::bad_alloc / std::length_error or a multi-gigabyte allocation
+        {
+            const size_t on_disk_max = file_size > (size_t)ftell(fp.f) ? file_size - (size_t)ftell(fp.f) : 0;
+            const size_t bytes_needed = qblock ? count / 32 * (size_t)qblock : count * (ttype == 0 ? 4 : 2);
+            bool overflow = false;
+            size_t chk = 1;
+            for (int i = 0; i < n_dims; ++i) { if (chk > SIZE_MAX / 8 / (size_t)ne[i]) overflow = true; chk *= (size_t)ne[i]; }
+            if (overflow || bytes_needed > on_disk_max) { err = "tensor " + name + " is larger than the rest of the file"; return false; }
+        }
         HostTensor t;
         t.ttype = ttype;
         for (int i = n_dims - 1; i >= 0; --i) t.shape.push_back(ne[i]);  // file stores innermost first

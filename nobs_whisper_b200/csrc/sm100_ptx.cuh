@@ -125,6 +125,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_mnmajor(uint32_t saddr) {
 // host side (gemm_sm100.cu)
 bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_inner,
                        uint32_t box_rows);
+// the same through a per-thread cache keyed by (pointer, shape, box): weights and lane activations never move, so the
+// driver call (cuTensorMapEncodeTiled, ~1 us) leaves the decode loop's host path
+bool get_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_inner,
+                      uint32_t box_rows);
 void sm100_set_error(const std::string& e);
 
 }  // namespace nobs

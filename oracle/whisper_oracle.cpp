@@ -949,6 +949,8 @@ int wo_lang_detect(wo_ctx* c, float* probs_out) {
 }
 
 // ---- whisper_full_with_state
+constexpr int kDeltaMin = 10;  // frames (100 ms): minimum audio whisper_full still processes
+
 int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
     wo_params p = *pp;
     const Vocab& vocab = c->model.vocab;
@@ -963,7 +965,9 @@ int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
     }
     const int seek_start = 0;
     const int seek_end = c->mel.n_len_org;
-    if (seek_end < seek_start + 100) return 0;
+    // shorter than 100 ms (delta_min = 10 frames): nothing to do.  whisper.cpp v1.7.x (the snapshot whisper-rs-sys 0.14.1 vendors)
+    // lowered this from 1 s; the reference app sends every clip longer than 1600 samples (state.rs:749)
+    if (seek_end < seek_start + kDeltaMin) return 0;
 
     std::vector<float> temperatures;
     if (p.temperature_inc > 0.0f) for (float t = p.temperature; t < 1.0f + 1e-6f; t += p.temperature_inc) temperatures.push_back(t);
@@ -1005,7 +1009,7 @@ int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
     std::vector<Cand> cands;
 
     while (true) {
-        if (seek + 100 >= seek_end) break;
+        if (seek + kDeltaMin >= seek_end) break;
         if (wo_encode(c, seek) != 0) return -6;
         if (seek > seek_start && seek + 500 >= seek_end) prompt_past.clear();
         int best_decoder_id = 0;
@@ -1106,9 +1110,9 @@ int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
                         d.has_ts = true;
                     }
                     if (tok.id == vocab.token_eot || (p.max_tokens > 0 && i >= p.max_tokens) ||
-                        (d.has_ts && seek + d.seek_delta + 100 >= seek_end)) {
+                        (d.has_ts && seek + d.seek_delta + kDeltaMin >= seek_end)) {
                         if (result_len == 0 && !p.no_timestamps) {
-                            if (seek + d.seek_delta + 100 >= seek_end) result_len = i + 1;
+                            if (seek + d.seek_delta + kDeltaMin >= seek_end) result_len = i + 1;
                             else { d.failed = true; continue; }
                         }
                         if (p.single_segment || p.no_timestamps) { result_len = i + 1; d.seek_delta = 100 * CHUNK_SIZE; }

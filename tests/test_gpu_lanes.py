@@ -40,9 +40,9 @@ def test_fp32_results_do_not_depend_on_the_lane_count(model_dir, kw):
     from nobs_whisper_b200 import ggml_synth, synth_audio
     from oracle import oracle
     path = ggml_synth.ensure_model(model_dir, "micro", init="fanin")
-    # 30-s windows, short clips, one under 1 s (no output) and a 75-s recording that needs three sequential windows
+    # 30-s windows, short clips, one under 1 s, one under 100 ms (no output) and a 75-s recording that needs three sequential windows
     # (its later windows are encoded while the other lanes keep decoding)
-    clips = [synth_audio.synth_clip(70 + i, s) for i, s in enumerate([30.0, 12.0, 75.0, 0.4, 21.0, 30.0, 5.0])]
+    clips = [synth_audio.synth_clip(70 + i, s) for i, s in enumerate([30.0, 12.0, 75.0, 0.4, 21.0, 30.0, 5.0, 0.06])]
     one = run_batch(nw, path, "fp32", 1, clips, **kw)
     for lanes in (2, 3):
         assert run_batch(nw, path, "fp32", lanes, clips, **kw) == one

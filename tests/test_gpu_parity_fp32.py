@@ -235,9 +235,16 @@ def test_short_and_empty_inputs(env):
     st = ctx.create_state()
     with pytest.raises(nw.WhisperError):
         st.full(ref_params(nw), np.zeros(0, np.float32))       # whisper-rs rejects an empty slice
-    st.full(ref_params(nw), np.zeros(8000, np.float32))         # < 1 s: returns 0 segments
+    st.full(ref_params(nw), np.zeros(1200, np.float32))         # < 100 ms (delta_min): returns 0 segments
     assert st.full_n_segments() == 0
-    assert orc.full(env.oracle.reference_params("en"), np.zeros(8000, np.float32)) == []
+    assert orc.full(env.oracle.reference_params("en"), np.zeros(1200, np.float32)) == []
+    # 0.1 s .. 1 s: the reference app sends every clip longer than 1600 samples (state.rs:749) and expects text back
+    for seed, secs in ((31, 0.5), (32, 0.12), (33, 0.99)):
+        short = env.synth.synth_clip(seed, secs)
+        st.full(ref_params(nw), short)
+        want = orc.full(env.oracle.reference_params("en"), short)
+        assert (len(want) > 0) == (secs > 0.2)      # 0.5 s and 0.99 s come back as one segment each; the 0.12-s clip decodes to nothing
+        _compare_segments(st.segments(), want)
     pcm = np.zeros(16000 * 4, np.float32)                        # silence
     st.full(ref_params(nw), pcm)
     _compare_segments(st.segments(), orc.full(env.oracle.reference_params("en"), pcm))

@@ -1,0 +1,11 @@
+#!/bin/bash
+# gpurun with retries while the pod answers "busy / draining" (exit code 3, nothing charged)
+# usage: tools/gpurun_retry.sh <timeout-seconds> '<command>' [gpus]
+T=$1; CMD=$2; G=${3:-1}
+for i in $(seq 1 12); do
+  if [ "$G" = "1" ]; then /usr/local/graft/bin/gpurun --timeout $T -- "$CMD"; else /usr/local/graft/bin/gpurun --gpus $G --timeout $T -- "$CMD"; fi
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  echo "[retry] attempt $i answered busy; sleeping 120 s"; sleep 120
+done
+exit 3
