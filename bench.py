@@ -11,6 +11,8 @@ One "step" = one pass of the hot path (mel -> encoder -> cross-KV -> decoder loo
 fallback -> segment text) over the rank's 120 windows.  N > 1: one process per GPU, every rank
 transcribes its own 120 windows (weak scaling, no collective on the data path; only a barrier
 and a max-reduce of the times), `value` = all ranks' audio-seconds / max-over-ranks time.
+`--scaling strong` splits ONE hour (120 windows in total, BASELINE config 4 as written) over the ranks
+with sharding.shard_range instead (15 windows per GPU at N = 8: a latency-bound decoder batch).
 
   value  : inputs already resident in HBM (device PCM), timed on the device-side wall
            (barrier + cuda synchronize both sides)
@@ -126,6 +128,13 @@ def ensure_model(arch: str, rank: int, world: int, barrier) -> str:
     return path
 
 
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_audio(n_windows: int, first: int):
     from nobs_whisper_b200 import synth_audio
     return [synth_audio.synth_clip(first + i, WINDOW_S) for i in range(n_windows)]
@@ -160,7 +169,10 @@ def run_reference(args, rank, world, arch_name):
     from oracle import oracle
     path = ensure_model(arch_name, 0, 1, lambda: None)
     orc = oracle.Oracle(path)
-    cores = oracle.lib().wo_max_threads()
+    # all the host threads this process may use; torchrun exports OMP_NUM_THREADS=1 to its workers, which must not
+    # decide the CPU arm's speed (rank 0 is the only rank that works here)
+    cores = host_cores()
+    oracle.lib().wo_set_threads(cores)
     n_sample = args.cpu_windows
     audio = make_audio(n_sample, 0)
     prm = oracle.reference_params("en")
@@ -174,7 +186,8 @@ def run_reference(args, rank, world, arch_name):
             times.append(dt)
     total = sum(times)
     value = args.steps * n_sample * WINDOW_S / total
-    sample = f"{n_sample} window(s) of {WINDOW_S:.0f} s per step (of the 120-window workload), oracle port of the whisper-rs CPU path, fp32"
+    sample = (f"{n_sample} window(s) of {WINDOW_S:.0f} s per step (of the 120-window workload), oracle port of the whisper-rs CPU path, fp32, "
+              f"{cores} OpenMP threads; the port's GEMM is a plain OpenMP-SIMD loop, not ggml's tuned CPU kernels")
     line = {
         "impl": "reference", "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -199,7 +212,11 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-windows", type=int, default=1, help="bounded sample for the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--latency-clips", type=int, default=24, help="5-s utterances for the large-v3-turbo latency figure (0: skip)")
+    ap.add_argument("--no-cpu-4threads", action="store_true", help="skip the second cpu_baseline pass at the upstream default of 4 threads")
+    ap.add_argument("--latency-clips", type=int, default=200, help="5-s utterances for the large-v3-turbo latency figure (0: skip); BASELINE config 5 asks for >= 200")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU transcribes its own --windows windows; strong: --windows windows in total (BASELINE config 4: one hour = 120 windows), "
+                         "rank r takes shard_range(windows, world, r)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,8 +254,15 @@ def main():
     eng.load_model(path)
     eng.set_profiling(True)
 
-    n_win = args.windows
-    audio = make_audio(n_win, rank * n_win)
+    from nobs_whisper_b200.sharding import shard_range
+    if args.scaling == "strong":
+        mine = shard_range(args.windows, world, rank)      # contiguous block of the ONE workload
+        n_win, first = len(mine), (mine[0] if len(mine) else 0)
+        total_windows = args.windows
+    else:
+        n_win, first = args.windows, rank * args.windows
+        total_windows = args.windows * world
+    audio = make_audio(n_win, first)
     n_samples = [len(a) for a in audio]
     # pinned host copies (e2e arm) and device copies (HBM-resident arm)
     host = [torch.from_numpy(a).pin_memory() for a in audio]
@@ -288,7 +312,7 @@ def main():
     dt_e2e, agg_e2e, texts = timed(host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
 
-    audio_s_per_step = n_win * WINDOW_S * world
+    audio_s_per_step = total_windows * WINDOW_S
     value = args.steps * audio_s_per_step / dt_dev
     e2e = args.steps * audio_s_per_step / dt_e2e
 
@@ -304,13 +328,24 @@ def main():
             from oracle import oracle
             orc = oracle.Oracle(path)
             prm = oracle.reference_params("en")
-            t0 = time.perf_counter()
-            for a in audio[: args.cpu_windows]:
-                orc.full(prm, a)
-            cdt = time.perf_counter() - t0
-            cpu_baseline = {"value": args.cpu_windows * WINDOW_S / cdt, "unit": "audio-s/s", "cores": oracle.lib().wo_max_threads(), "kind": "port",
+            cores = host_cores()
+
+            def cpu_run(threads):
+                oracle.lib().wo_set_threads(threads)
+                t0 = time.perf_counter()
+                for a in audio[: args.cpu_windows]:
+                    orc.full(prm, a)
+                return time.perf_counter() - t0
+
+            cdt = cpu_run(cores)
+            cpu_baseline = {"value": args.cpu_windows * WINDOW_S / cdt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                             "sample": f"first {args.cpu_windows} of the {n_win} windows ({args.cpu_windows * WINDOW_S:.0f} s of audio), oracle port of the "
-                                      f"whisper-rs CPU path in fp32, {cdt:.1f} s of CPU work"}
+                                      f"whisper-rs CPU path in fp32 (plain OpenMP-SIMD GEMM loops, not ggml's tuned kernels), {cdt:.1f} s of CPU work"}
+            if not args.no_cpu_4threads and cores > 4:
+                # the reference never calls set_n_threads (whisper.rs:88-124): it inherits upstream's n_threads = min(4, hw)
+                cdt4 = cpu_run(4)
+                cpu_baseline["at_4_threads"] = {"value": args.cpu_windows * WINDOW_S / cdt4, "unit": "audio-s/s", "cores": 4,
+                                                "note": "upstream default n_threads = min(4, hw), which the reference inherits", "cpu_s": cdt4}
             orc.close()
         steps = args.steps
         # Dominant kernel of the step: the decoder's cross-attention stream over the cross-KV panels
@@ -357,12 +392,14 @@ def main():
             latency = turbo_latency(args.latency_clips)
         line = {
             "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {
                 "workload": f"whisper {args.model} ({arch.n_mels} mel bins, {arch.n_audio_layer}+{arch.n_text_layer} layers) {args.precision}, "
-                            f"{n_win} x 30-s windows per GPU (1 h synthetic 16 kHz audio), greedy best_of=1 with the reference's temperature fallback",
-                "windows_per_gpu": n_win, "weights": "random-init N(0,0.02) ggml f16 file, seed 0", "l2": "inputs and weights exceed L2 (3.1 GB weights, 30 GB cross-KV)",
+                            + (f"{n_win} x 30-s windows per GPU (1 h of synthetic 16 kHz audio each; weak scaling)" if args.scaling == "weak" else
+                               f"{total_windows} x 30-s windows in total split over {world} GPU(s) ({n_win} on rank 0; strong scaling of the one-hour workload)")
+                            + ", greedy best_of=1 with the reference's temperature fallback",
+                "windows_per_gpu": n_win, "windows_total": total_windows, "weights": "random-init N(0,0.02) ggml f16 file, seed 0", "l2": "inputs and weights exceed L2 (3.1 GB weights, 30 GB cross-KV)",
                 "decoder_rows_per_step": agg_dev["rows"] / steps, "sampled_tokens_per_step": agg_dev["samples"] / steps,
                 "decoder_rounds_per_step": agg_dev["rounds"] / steps, "fallbacks_per_step": agg_dev["fallbacks"] / steps,
                 "stage_ms_per_step": {"mel": agg_dev["ms_mel"] / steps, "encode": agg_dev["ms_enc"] / steps,
@@ -370,7 +407,7 @@ def main():
                 "x_realtime": value, "timing": "CUDA events on the library stream around the K steps, max over ranks",
                 "host_wall_ms_per_step": 1000.0 * agg_dev["wall_s"] / steps,
             },
-            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int(agg_e2e["d2h"] / steps) * world,
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(total_windows * WINDOW_S * 16000 * 4), "d2h_bytes_per_step": int(agg_e2e["d2h"] / steps) * world,
                     "ms_per_step": 1000.0 * dt_e2e / steps},
             "gpu_launches": int(agg_dev["launches"] + agg_e2e["launches"]),
             "roofline": roofline,

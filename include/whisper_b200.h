@@ -296,12 +296,26 @@ struct whisper_context* whisper_b200_init_host_only(const char* path_model);
 int whisper_b200_full_batch(struct whisper_context* ctx, struct whisper_state* const* states, int n, struct whisper_full_params params,
                             const float* const* samples, const int* n_samples, int* rc);
 
+/* The same with one initial_prompt per audio (NULL entries: params.initial_prompt): what the reference's chunk chaining needs
+ * when chunks are decoded together (whisper.rs:165-180 puts the previous chunk's text into the next chunk's prompt). */
+int whisper_b200_full_batch_prompts(struct whisper_context* ctx, struct whisper_state* const* states, int n, struct whisper_full_params params,
+                                    const char* const* initial_prompts, const float* const* samples, const int* n_samples, int* rc);
+
 /* Batched whisper_decode_with_state: ONE decoder round over n states (each already encoded: whisper_encode_with_state).
  * State i contributes n_tokens[i] token rows (tokens are concatenated in `tokens`) at positions n_past[i].. ; the logits of its
  * last row are written to logits_out[i * n_vocab .. ] (fp32).  All rows run in the same launches (the decode-lane path `full`
  * uses, on lane `lane`), so this is the stage-level hook for teacher-forced parity checks of step batches.  0 on success. */
 int whisper_b200_decode_batch(struct whisper_context* ctx, struct whisper_state* const* states, int n, const whisper_token* tokens,
                               const int* n_tokens, const int* n_past, int lane, float* logits_out);
+
+/* Scripted-logits test hook (known-answer tests of the control flow, tests/test_control_flow_kat.py): while set, `whisper_full*`
+ * offers the logits of every row it is about to sample from to `hook` BEFORE the decoder round is queued: seek of the window
+ * (10 ms units), temperature index, step = index of the token about to be sampled (0: sampled from the prompt), decoder index,
+ * number of prompt rows of this pass.  If hook returns non-zero, what it wrote to logits[n_vocab] replaces the model's logits of
+ * that row on the device (the filter / log-softmax / sampling kernel then runs on them); 0 keeps the model's logits.  NULL removes
+ * the hook.  Not meant for production use. */
+typedef int (*whisper_b200_logits_hook)(void* user, int seek, int i_temp, int step, int decoder, int n_prompt, int n_vocab, float* logits);
+void whisper_b200_set_logits_hook(struct whisper_context* ctx, whisper_b200_logits_hook hook, void* user);
 
 /* Copy of the normalised log-mel of the last pcm_to_mel/full call, upstream layout
  * [n_mel][n_len]; returns n_len (or the needed float count negated if cap is too small). */
@@ -369,6 +383,10 @@ int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n
 /* Micro-benchmark hook: average device microseconds per launch of the decoder-step kernels for R token
  * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..12]; out_us holds 16 floats). */
 int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us);
+/* Micro-benchmark of the device-wide barrier of the fused projection chains: microseconds per barrier over `ctas` CTAs;
+ * variant 0 fence + atomic + nanosleep polling, 1 without nanosleep, 2 acq_rel atomic / release increment / acquire polling;
+ * store_floats fp32 stores per thread in front of every barrier. */
+int whisper_b200_debug_grid_sync(int ctas, int iters, int variant, int store_floats, float* us_per_barrier);
 
 /* ---- silence chunker (reference src-tauri/src/audio.rs) ----------------------------------
  * Cuts a long 16 kHz recording into the pieces the transcription path consumes (reference state.rs:757-780).
@@ -441,6 +459,13 @@ int nobs_engine_transcribe_recording(struct nobs_engine* e, const float* audio, 
                                      const char** out);
 /* Data-parallel variant of transcribe for independent windows: no context
  * chaining; texts[i] receives pointers owned by the engine. */
+/* whisper.rs:152-197 with the chunks decoded data-parallel: same result as nobs_engine_transcribe_chunked (chunk k's prompt carries
+ * the text of the last non-empty chunk before it), obtained by speculative batches — decode a window of chunks together with the
+ * context known so far, accept the longest prefix whose context turned out right, re-decode the rest.  abort_on_error = 1: stop at
+ * the first failing chunk (whisper.rs:182-185); 0: skip it (state.rs:773-775).  n_decodes / n_rounds (optional): chunk decodes and
+ * batched rounds spent (n_chunks decodes = no speculation wasted). */
+int nobs_engine_transcribe_chunked_parallel(struct nobs_engine* e, const float* const* chunks, const int* n, int n_chunks, const char* language,
+                                            const char* vocabulary, int abort_on_error, const char** out, int* n_decodes, int* n_rounds);
 int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audios, const int* n, int n_audios, const char* language,
                                  const char* vocabulary, int beam_size, const char** texts);
 const char* nobs_engine_last_error(struct nobs_engine* e);

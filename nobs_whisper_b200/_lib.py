@@ -16,14 +16,43 @@ CSRC = os.path.join(_HERE, "csrc")
 WHISPER_MAX_DECODERS = 8
 
 
+def source_hash() -> str:
+    """sha256 over every file the shared library is compiled from (sources, headers, Makefile)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = []
+    for root, _, names in os.walk(CSRC):
+        if os.path.basename(root) == "build" or os.sep + "build" + os.sep in root + os.sep:
+            continue
+        files += [os.path.join(root, n) for n in names if n.endswith((".cu", ".cuh", ".cpp", ".h")) or n == "Makefile"]
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "whisper_b200.h"))
+    for f in sorted(files):
+        h.update(os.path.relpath(f, _HERE).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """Compile every CUDA / C++ source for sm_100a into the in-tree shared library."""
-    cmd = ["make", "-C", CSRC, "-j8"]
+    """Compile every CUDA / C++ source for sm_100a into the in-tree shared library (csrc/Makefile:
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo).  force: clean rebuild.  A record of what was
+    done (mode, seconds, source hash) is left in csrc/build/build_record.json."""
+    import json
+    import time
+    t0 = time.time()
     if force:
         subprocess.check_call(["make", "-C", CSRC, "clean"], stdout=subprocess.DEVNULL)
-    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    before = os.path.getmtime(LIB_PATH) if os.path.exists(LIB_PATH) else None
+    subprocess.check_call(["make", "-C", CSRC, "-j8"], stdout=subprocess.DEVNULL)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("build did not produce " + LIB_PATH)
+    compiled = before is None or os.path.getmtime(LIB_PATH) != before
+    rec = {"build_mode": "clean" if force else "incremental", "build_exercised": bool(compiled), "seconds": round(time.time() - t0, 1),
+           "source_sha256": source_hash(), "library": os.path.relpath(LIB_PATH, os.path.dirname(_HERE)), "library_bytes": os.path.getsize(LIB_PATH),
+           "flags": "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17"}
+    os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    with open(os.path.join(CSRC, "build", "build_record.json"), "w") as f:
+        json.dump(rec, f, indent=1)
     return LIB_PATH
 
 
@@ -114,6 +143,8 @@ class B200Stats(C.Structure):
 
 
 vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+# int hook(user, seek, i_temp, step, decoder, n_prompt, n_vocab, logits*): whisper_b200_logits_hook
+LOGITS_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float))
 
 # name -> (restype, argtypes); every symbol include/whisper_b200.h declares
 SIGNATURES = {
@@ -181,7 +212,9 @@ SIGNATURES = {
     "whisper_b200_precision": (C.c_int, [vp]),
     "whisper_b200_decode_lanes": (C.c_int, [vp]),
     "whisper_b200_init_host_only": (vp, [C.c_char_p]),
+    "whisper_b200_set_logits_hook": (None, [vp, LOGITS_HOOK, vp]),
     "whisper_b200_decode_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int32), ip, ip, C.c_int, fp]),
+    "whisper_b200_full_batch_prompts": (C.c_int, [vp, C.POINTER(vp), C.c_int, WhisperFullParams, C.POINTER(C.c_char_p), C.POINTER(fp), ip, ip]),
     "whisper_b200_full_batch": (C.c_int, [vp, C.POINTER(vp), C.c_int, WhisperFullParams, C.POINTER(fp), ip, ip]),
     "whisper_b200_get_mel": (C.c_int, [vp, fp, C.c_size_t]),
     "whisper_b200_get_encoder_output": (C.c_int, [vp, vp, fp, C.c_size_t]),
@@ -195,6 +228,7 @@ SIGNATURES = {
     "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
     "whisper_b200_debug_dec_cross_attention": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, C.c_int]),
     "whisper_b200_debug_time_decode_kernels": (C.c_int, [C.c_int, C.c_int, C.c_int, fp]),
+    "whisper_b200_debug_grid_sync": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "whisper_b200_window_rms": (C.c_int, [fp, C.c_size_t, C.c_uint32, fp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nobs_find_silence_boundaries": (C.c_int, [fp, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t)]),
     "nobs_split_at_silences_with_overlap": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t),
@@ -226,6 +260,7 @@ SIGNATURES = {
     "nobs_engine_transcribe": (C.c_int, [vp, fp, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]),
     "nobs_engine_transcribe_chunked": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p)]),
     "nobs_engine_transcribe_recording": (C.c_int, [vp, fp, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
+    "nobs_engine_transcribe_chunked_parallel": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), ip, ip]),
     "nobs_engine_transcribe_batch": (C.c_int, [vp, C.POINTER(fp), ip, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]),
     "nobs_engine_last_error": (C.c_char_p, [vp]),
     "nobs_engine_last_stats": (C.c_int, [vp, C.POINTER(B200Stats)]),

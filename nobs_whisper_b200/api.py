@@ -205,6 +205,21 @@ class WhisperContext:
             raise WhisperError("tokenize failed")
         return list(buf[:m])
 
+    def set_logits_hook(self, fn):
+        """Scripted-logits test hook (whisper_b200_set_logits_hook): fn(seek, i_temp, step, decoder, n_prompt, logits: np.ndarray view)
+        returns truthy if it overwrote the logits of that sample row; None removes the hook."""
+        L = _lib.lib()
+        if fn is None:
+            L.whisper_b200_set_logits_hook(self._h, C.cast(None, _lib.LOGITS_HOOK), None)
+            self._hook = None
+            return
+
+        def tramp(_user, seek, it, step, dec, n_prompt, n_vocab, ptr):
+            return 1 if fn(seek, it, step, dec, n_prompt, np.ctypeslib.as_array(ptr, shape=(n_vocab,))) else 0
+
+        self._hook = _lib.LOGITS_HOOK(tramp)     # keep the trampoline alive
+        L.whisper_b200_set_logits_hook(self._h, self._hook, None)
+
     def process_logits(self, params: FullParams, logits, hist=(), has_ts=False, seek_delta=3000, temperature=0.0, mode=0, u=0.0, k=0):
         """Stage hook: K6 (filter + log-softmax + sampling) on explicit logits."""
         L = _lib.lib()

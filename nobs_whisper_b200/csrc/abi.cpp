@@ -209,6 +209,25 @@ int whisper_b200_full_batch(struct whisper_context* ctx, struct whisper_state* c
     return -100;
 }
 
+int whisper_b200_full_batch_prompts(struct whisper_context* ctx, struct whisper_state* const* states, int n, struct whisper_full_params params,
+                                    const char* const* initial_prompts, const float* const* samples, const int* n_samples, int* rc) {
+    if (!ctx || !states || !samples || !n_samples || !rc || n <= 0) { set_last_error("bad arguments"); return -100; }
+    if (!ctx->engine) { set_last_error("this context has no GPU engine (host-only handle); there is no CPU fallback"); return -100; }
+    for (int i = 0; i < n; ++i) {
+        if (!states[i] || states[i]->ctx != ctx || (n_samples[i] > 0 && !samples[i])) { set_last_error("bad state/audio in batch"); return -100; }
+        for (int k = 0; k < i; ++k) if (states[k] == states[i]) { set_last_error("a state appears twice in the batch"); return -100; }
+    }
+    try {
+        return full_batch(ctx, states, n, params, samples, n_samples, rc, initial_prompts);
+    } catch (const std::exception& e) {
+        set_last_error(std::string("full: ") + e.what());
+    } catch (...) {
+        set_last_error("full: unknown exception");
+    }
+    for (int i = 0; i < n; ++i) rc[i] = -100;
+    return -100;
+}
+
 int whisper_full_with_state(struct whisper_context* ctx, struct whisper_state* state, struct whisper_full_params params,
                             const float* samples, int n_samples) {
     int rc = 0;
@@ -361,6 +380,13 @@ int whisper_b200_decode_batch(struct whisper_context* ctx, struct whisper_state*
         return -1;
     }
     return 0;
+}
+void whisper_b200_set_logits_hook(struct whisper_context* ctx, whisper_b200_logits_hook hook, void* user) {
+    if (!ctx) return;
+    std::unique_lock<std::mutex> lock;
+    if (ctx->engine) lock = std::unique_lock<std::mutex>(ctx->engine->mu);
+    ctx->logits_hook = hook;
+    ctx->logits_hook_user = user;
 }
 float* whisper_get_logits_from_state(struct whisper_state* st) { return st && !st->logits.empty() ? st->logits.data() : nullptr; }
 

@@ -7,6 +7,7 @@
 
 #include "../../include/whisper_b200.h"
 #include "gemm_sm100.cuh"
+#include "grid_sync.cuh"
 
 namespace nobs { void set_last_error(const std::string& e); }
 using namespace nobs;
@@ -236,5 +237,43 @@ extern "C" int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, f
     const cudaError_t err = cudaStreamSynchronize(s);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
     if (err != cudaSuccess) { set_last_error(std::string("debug_time: ") + cudaGetErrorString(err)); return -4; }
+    return 0;
+}
+
+// Micro-benchmark of the device-wide barrier used by the fused projection chains: `iters` barriers over `ctas` CTAs of 256 threads;
+// before every barrier each thread stores store_floats fp32 values (emulates the partial-sum burst in front of the real barrier).
+namespace {
+template <int V>
+__global__ void __launch_bounds__(256, 1) grid_sync_bench_kernel(unsigned int* bar, float* scratch, int store_floats, int iters) {
+    unsigned int gen = nobs::gs_ld_acquire(&bar[1]);
+    float* mine = scratch + ((size_t)blockIdx.x * 256 + threadIdx.x) * (size_t)(store_floats > 0 ? store_floats : 1);
+    for (int it = 0; it < iters; ++it) {
+        for (int k = 0; k < store_floats; ++k) mine[k] = (float)(it + k);
+        nobs::grid_sync_v<V>(bar, gridDim.x, gen);
+    }
+}
+}  // namespace
+extern "C" int whisper_b200_debug_grid_sync(int ctas, int iters, int variant, int store_floats, float* us_per_barrier) {
+    if (ctas <= 0 || ctas > 148 || iters <= 0 || !us_per_barrier || store_floats < 0 || store_floats > 256) return -1;
+    DevBuf bar, scratch;
+    if (!bar.alloc(256) || !scratch.alloc((size_t)ctas * 256 * (store_floats > 0 ? store_floats : 1) * 4)) return -2;
+    cudaMemset(bar.p, 0, 256);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&](int n) {
+        if (variant == 0) grid_sync_bench_kernel<0><<<ctas, 256>>>((unsigned int*)bar.p, (float*)scratch.p, store_floats, n);
+        else if (variant == 1) grid_sync_bench_kernel<1><<<ctas, 256>>>((unsigned int*)bar.p, (float*)scratch.p, store_floats, n);
+        else grid_sync_bench_kernel<2><<<ctas, 256>>>((unsigned int*)bar.p, (float*)scratch.p, store_floats, n);
+    };
+    run(10);
+    cudaEventRecord(e0);
+    run(iters);
+    cudaEventRecord(e1);
+    const cudaError_t err = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) { set_last_error(std::string("debug_grid_sync: ") + cudaGetErrorString(err)); return -4; }
+    *us_per_barrier = 1e3f * ms / iters;
     return 0;
 }

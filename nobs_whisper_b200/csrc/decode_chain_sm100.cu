@@ -32,6 +32,7 @@
 #include <string>
 
 #include "device_utils.cuh"
+#include "grid_sync.cuh"
 #include "sm100_ptx.cuh"
 
 namespace nobs {
@@ -57,35 +58,13 @@ struct ChainMaps {
 
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) { return gs_ld_acquire(p); }
 
-// Device-wide barrier over the G CTAs of this grid: bar[0] arrival counter, bar[1] generation.  Self-resetting
-// (the last arriver zeroes the counter before it bumps the generation), so consecutive kernels of one lane share it.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int G, unsigned int& gen) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int old = atomicAdd(&bar[0], 1u);
-        if (old == G - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(&bar[1]) == gen) {
-                __nanosleep(32);
-                if (clock64() - t0 > 4000000000LL) __trap();   // a protocol error must be a launch failure, not a hung GPU
-            }
-        }
-        __threadfence();
-    }
-    gen += 1;
-    __syncthreads();
-}
+// barrier flavour (grid_sync.cuh); chosen from the micro-benchmark (whisper_b200_debug_grid_sync)
+#ifndef NOBS_CHAIN_SYNC_VARIANT
+#define NOBS_CHAIN_SYNC_VARIANT 2
+#endif
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int G, unsigned int& gen) { grid_sync_v<NOBS_CHAIN_SYNC_VARIANT>(bar, G, gen); }
 
 template <typename T> __device__ __forceinline__ void ch_store4(T* p, const float (&v)[4]);
 template <> __device__ __forceinline__ void ch_store4<bf16>(bf16* p, const float (&v)[4]) {
@@ -339,11 +318,13 @@ dec_chain_sm100_kernel(const __grid_constant__ ChainMaps maps, const __grid_cons
         }
         if (has) acc_phase ^= 1;
         if (st.reduce) {
+            if (g_trace) { __syncthreads(); trace_end(trace_begin(130 + s, cd.partial)); }   // this CTA's share of the GEMM is done
             grid_sync(cd.bar, G, gen);           // every partial sum of this step is in the workspace
             tc_fence_after();
             trace_end(trace_begin(110 + s, cd.partial));
             for (int r = cta; r < R; r += (int)G) chain_reduce_row(st.e, r, red);
             fence_proxy_async_global();          // the next step reads y / h through TMA (async proxy)
+            if (g_trace) { __syncthreads(); trace_end(trace_begin(140 + s, cd.partial)); }   // this CTA's rows are reduced
             grid_sync(cd.bar, G, gen);
             trace_end(trace_begin(120 + s, cd.partial));
         }

@@ -392,7 +392,7 @@ public:
     }
 
     bool decode_submit(int lane, const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
-                       float* logits_host) override {
+                       float* logits_host, const float* inject, const unsigned char* inject_mask) override {
         CUDA_OK(cudaSetDevice(device_));
         if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "decode: no such lane"; return false; }
         Lane& L = lanes_[lane];
@@ -425,7 +425,8 @@ public:
             if (r1 == r0) { err_ = "decode: cannot make progress"; L.inflight = false; return false; }
             const bool last = r1 == rows.size();
             if (!decode_chunk(L, rows.data() + r0, (int)(r1 - r0), sample_rows.data() + si, (int)(sj - si), (int)r0, sp.data() + si, si,
-                              logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr)) { L.inflight = false; return false; }
+                              logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr, inject ? inject + si * (size_t)hp_.n_vocab : nullptr,
+                              inject_mask ? inject_mask + si : nullptr)) { L.inflight = false; return false; }
             if (!last && !finish_chunk(L)) { L.inflight = false; return false; }
             si = sj;
             r0 = r1;
@@ -707,7 +708,7 @@ public:
     // Queues one chunk of rows on the lane; its sample results land in the lane's pinned staging
     // (finish_chunk picks them up after the stream has drained).
     bool decode_chunk(Lane& Ln, const RowDesc* rows, int R, const int* samp, int S, int row_base, const SampleParams* sp, size_t res_off,
-                      float* logits_host) {
+                      float* logits_host, const float* inject = nullptr, const unsigned char* inject_mask = nullptr) {
         const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
         cudaStream_t st = Ln.stream;
         for (int r = 0; r < R; ++r) {
@@ -777,6 +778,12 @@ public:
             mark_begin(Ln.tm, detail_);
             launch_layernorm_gather<T>(Ln.x, d, didx, dec_ln_g_, dec_ln_b_, Ln.ys, d, S, d, st);
             if (!logits_gemm(Ln, S)) return false;
+            if (inject && inject_mask) {   // scripted-logits test hook: pageable source, staged by the runtime before the call returns
+                for (int i = 0; i < S; ++i)
+                    if (inject_mask[i])
+                        CUDA_OK(cudaMemcpyAsync(Ln.logits + (size_t)i * hp_.n_vocab, inject + (size_t)i * hp_.n_vocab, sizeof(float) * hp_.n_vocab,
+                                                cudaMemcpyHostToDevice, st));
+            }
             launch_process_logits(Ln.logits, hp_.n_vocab, dsp, dres, S, vocab_ids, nullptr, Ln.probs, st);
             mark_end(Ln.tm, detail_, 15);
             CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, st));
@@ -1154,7 +1161,9 @@ private:
         // fused projection chains need every lane's chain grid co-resident (decode_chain_sm100.cu); otherwise the
         // multi-launch path runs
         chain_stages_ = env_int("NOBS_WHISPER_CHAIN_STAGES", chain_stages_for_lanes(n_lanes));
-        use_chain_ = env_int("NOBS_WHISPER_CHAIN", 1) != 0 && !f32 && chain_fits(n_lanes, chain_stages_);
+        // Off by default: measured on B200 (profiles/r2_chain_*.txt) a device-wide barrier costs 1.9 us — the same as a PDL launch
+        // boundary — and the chain needs two per projection, so the fused grid is ~5 % SLOWER than twelve small launches.
+        use_chain_ = env_int("NOBS_WHISPER_CHAIN", 0) != 0 && !f32 && chain_fits(n_lanes, chain_stages_);
         // The encoder and every decode lane own their activations: a lane may decode while the encoder
         // works on other windows and while other lanes decode.
         auto plan_enc = [&](Arena& a) {

@@ -86,8 +86,9 @@ public:
     virtual int n_lanes() const = 0;
     // rows: token rows in order; sample_rows[i] indexes `rows`; one SampleParams per sample row.
     // logits_host (optional): receives [n_sample][n_vocab] raw logits.  Returns once the work is queued.
+    // inject / inject_mask (optional, test hook): inject[i * n_vocab ..] replaces the logits of sample i on the device where inject_mask[i] != 0.
     virtual bool decode_submit(int lane, const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
-                               float* logits_host) = 0;
+                               float* logits_host, const float* inject = nullptr, const unsigned char* inject_mask = nullptr) = 0;
     // waits for the lane's round; one SampleResult per sample row
     virtual bool decode_collect(int lane, std::vector<SampleResult>& results) = 0;
     bool decode(const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,

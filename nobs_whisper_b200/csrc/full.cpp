@@ -107,13 +107,16 @@ class Driver {
         std::vector<SampleParams> sp;
         std::vector<SampleResult> res;
         std::vector<KvCopy> kv_pairs_a, kv_pairs_b;
+        std::vector<float> inject;             // scripted-logits test hook: replacement logits per sample of the round
+        std::vector<unsigned char> inject_mask;
         bool inflight = false;
     };
 
 public:
     Driver(whisper_context* ctx) : ctx_(ctx), eng_(*ctx->engine), vocab_(ctx->model.vocab), hp_(ctx->model.hp) {}
 
-    int run(whisper_state* const* states, int n, const whisper_full_params& params, const float* const* samples, const int* n_samples, int* rc) {
+    int run(whisper_state* const* states, int n, const whisper_full_params& params, const float* const* samples, const int* n_samples, int* rc,
+            const char* const* initial_prompts) {
         const long launches0 = kernel_launch_count();
         eng_.stats = EngineStats();
         jobs_.assign(n, Job());
@@ -123,6 +126,7 @@ public:
             Job& j = jobs_[i];
             j.st = states[i];
             j.p = params;
+            if (initial_prompts && initial_prompts[i]) j.p.initial_prompt = initial_prompts[i];   // per-audio prompt (chunk chaining under data parallelism)
             j.st->result_all.clear();
             j.st->stats = whisper_b200_stats{};
             j.st->encoded_seek = -1;
@@ -176,10 +180,13 @@ public:
                     if (!encode_round(L)) return fail_all(rc, n, -6);
                     L.rows.clear(); L.samp.clear(); L.sp.clear();
                     L.kv_pairs_a.clear(); L.kv_pairs_b.clear();
+                    L.inject_mask.clear();
                     bool any = false;
                     for (int i : L.jobs) any |= emit_rows(jobs_[i]);
                     if (any) {
-                        if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr)) return fail_all(rc, n, -8);
+                        const bool scripted = !L.inject_mask.empty();
+                        if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr, scripted ? L.inject.data() : nullptr, scripted ? L.inject_mask.data() : nullptr))
+                            return fail_all(rc, n, -8);
                         L.inflight = true;
                         active = true;
                         break;
@@ -355,6 +362,15 @@ private:
         }
     }
 
+    // Scripted-logits test hook (whisper_b200_set_logits_hook): called for the sample just appended to the lane's round.
+    void offer_logits(LaneState& L, const Job& j, int step, int decoder) {
+        if (!ctx_->logits_hook) return;
+        const size_t nv = (size_t)hp_.n_vocab, i = L.samp.size() - 1;
+        if (L.inject.size() < (i + 1) * nv) L.inject.resize((i + 1) * nv);
+        L.inject_mask.resize(i + 1, 0);
+        L.inject_mask[i] = ctx_->logits_hook(ctx_->logits_hook_user, j.seek, j.it, step, decoder, (int)j.prompt.size(), hp_.n_vocab, L.inject.data() + i * nv) ? 1 : 0;
+    }
+
     // Append this job's rows for the next decoder round.  Returns false if it has none.
     bool emit_rows(Job& j) {
         LaneState& L = lanes_[j.lane];
@@ -405,6 +421,7 @@ private:
                 fill_sample_params(j, j.dec[k], t_cur, /*prefill=*/k == 0, k, sp);
                 sp_.push_back(sp);
                 j.live.push_back(k);
+                offer_logits(L, j, /*step=*/0, k);
             }
             j.n_samples = j.n_cur;
             j.step = 0;
@@ -425,6 +442,7 @@ private:
                 fill_sample_params(j, d, t_cur, false, k, sp);
                 sp_.push_back(sp);
                 j.live.push_back(k);
+                offer_logits(L, j, j.step + 1, k);
             }
             j.n_samples = (int)j.live.size();
             st->stats.n_decode_rows += j.n_samples;
@@ -647,11 +665,11 @@ bool ensure_state_slots(whisper_context* ctx, whisper_state* st, int n_kv) {
 }
 
 int full_batch(whisper_context* ctx, whisper_state* const* states, int n, const whisper_full_params& params, const float* const* samples,
-               const int* n_samples, int* rc) {
+               const int* n_samples, int* rc, const char* const* initial_prompts) {
     if (!ctx || !ctx->engine || n <= 0) return -100;
     std::lock_guard<std::mutex> lock(ctx->engine->mu);
     Driver drv(ctx);
-    return drv.run(states, n, params, samples, n_samples, rc);
+    return drv.run(states, n, params, samples, n_samples, rc, initial_prompts);
 }
 
 }  // namespace nobs

@@ -232,7 +232,7 @@ WhisperError WhisperEngine::transcribe_chunked(const std::vector<std::vector<flo
 }
 
 WhisperError WhisperEngine::transcribe_recording(const float* audio, size_t n, const std::optional<std::string>& language,
-                                                 const std::optional<std::string>& vocabulary, bool parallel, std::string& out) const {
+                                                 const std::optional<std::string>& vocabulary, int parallel, std::string& out) const {
     out.clear();
     if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
     if (n <= 1600) return WhisperError{WhisperError::None, ""};   // state.rs:749: only audio longer than 0.1 s is transcribed
@@ -252,7 +252,18 @@ WhisperError WhisperEngine::transcribe_recording(const float* audio, size_t n, c
         pieces.emplace_back(0, n);
     }
     std::vector<std::string> results;
-    if (parallel && pieces.size() > 1) {
+    if (parallel == 2 && pieces.size() > 1) {
+        // the reference's loop (context chaining, failing pieces skipped), decoded data-parallel
+        std::vector<const float*> ptrs;
+        std::vector<int> lens;
+        for (const auto& p : pieces) { ptrs.push_back(audio + p.first); lens.push_back((int)(p.second - p.first)); }
+        const WhisperError e = transcribe_chunked_parallel(ptrs, lens, language, vocabulary, /*abort_on_error=*/false, out);
+        if (e.kind != WhisperError::None) return e;
+        const size_t b0 = out.find_first_not_of(" \t\r\n"), e0 = out.find_last_not_of(" \t\r\n");
+        out = b0 == std::string::npos ? std::string() : out.substr(b0, e0 - b0 + 1);
+        return WhisperError{};
+    }
+    if (parallel == 1 && pieces.size() > 1) {
         std::vector<const float*> ptrs;
         std::vector<int> lens;
         for (const auto& p : pieces) { ptrs.push_back(audio + p.first); lens.push_back((int)(p.second - p.first)); }
@@ -275,6 +286,122 @@ WhisperError WhisperEngine::transcribe_recording(const float* audio, size_t n, c
     }
     const size_t b = out.find_first_not_of(" \t\r\n"), e2 = out.find_last_not_of(" \t\r\n");   // .trim()
     out = b == std::string::npos ? std::string() : out.substr(b, e2 - b + 1);
+    return WhisperError{};
+}
+
+WhisperError WhisperEngine::transcribe_batch_contexts(const std::vector<const float*>& audios, const std::vector<int>& n,
+                                                      const std::optional<std::string>& language, const std::optional<std::string>& vocabulary,
+                                                      const std::vector<std::optional<std::string>>& contexts, std::vector<std::string>& out,
+                                                      std::vector<int>* rc_out) const {
+    out.clear();
+    if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
+    const int cnt = (int)audios.size();
+    if (cnt == 0) return WhisperError{};
+    if (n.size() != audios.size() || contexts.size() != audios.size()) return WhisperError{WhisperError::TranscriptionError, "audios / lengths / contexts size mismatch"};
+    std::vector<whisper_state*> states(cnt, nullptr);
+    auto free_states = [&]() { for (auto* s : states) whisper_free_state(s); };
+    std::vector<std::optional<std::string>> prompts(cnt);
+    std::vector<const char*> prompt_ptrs(cnt, nullptr);
+    for (int i = 0; i < cnt; ++i) {
+        if (!audios[i] || n[i] <= 0) { free_states(); return WhisperError{WhisperError::TranscriptionError, "Input sample buffer was empty."}; }
+        states[i] = whisper_init_state(ctx_);
+        if (!states[i]) { free_states(); return WhisperError{WhisperError::TranscriptionError, whisper_b200_last_error()}; }
+        prompts[i] = build_prompt(vocabulary, contexts[i]);                           // whisper.rs:98-105, per chunk
+        prompt_ptrs[i] = prompts[i] ? prompts[i]->c_str() : nullptr;
+    }
+    const whisper_full_params p = make_params(language, nullptr, 0);
+    std::vector<int> rc(cnt, 0);
+    const int r = whisper_b200_full_batch_prompts(ctx_, states.data(), cnt, p, prompt_ptrs.data(), audios.data(), n.data(), rc.data());
+    if (r != 0 && !rc_out) {
+        free_states();
+        return WhisperError{WhisperError::TranscriptionError, "whisper_b200_full_batch returned " + std::to_string(r) + ": " + whisper_b200_last_error()};
+    }
+    if (!rc_out) {
+        for (int i = 0; i < cnt; ++i)
+            if (rc[i] != 0) {
+                free_states();
+                return WhisperError{WhisperError::TranscriptionError, "whisper_b200_full_batch returned " + std::to_string(rc[i]) + ": " + whisper_b200_last_error()};
+            }
+    } else {
+        *rc_out = rc;
+        if (r != 0) for (auto& v : *rc_out) if (v == 0) v = r;
+    }
+    out.resize(cnt);
+    for (int i = 0; i < cnt; ++i) {
+        if (rc[i] == 0 && r == 0) out[i] = filter_hallucinations(trim(collect_text(states[i])));
+        accumulate_stats(states[i], i == 0);
+    }
+    free_states();
+    return WhisperError{};
+}
+
+WhisperError WhisperEngine::transcribe_chunked_parallel(const std::vector<const float*>& chunks, const std::vector<int>& n,
+                                                        const std::optional<std::string>& language, const std::optional<std::string>& vocabulary,
+                                                        bool abort_on_error, std::string& out, ChainStats* stats) const {
+    out.clear();
+    if (!ctx_) return WhisperError{WhisperError::NoModel, ""};
+    const int cnt = (int)chunks.size();
+    if (n.size() != chunks.size()) return WhisperError{WhisperError::TranscriptionError, "chunks / lengths size mismatch"};
+    ChainStats cs;
+    std::vector<std::string> text(cnt);                       // current transcript of every chunk
+    std::vector<int> status(cnt, -1);                         // -1 never decoded, 0 ok, > 0 failed
+    std::vector<std::optional<std::string>> used(cnt);        // the context chunk k was last decoded with
+    std::vector<std::string> err_text(cnt);
+    int final_upto = 0;                                       // chunks [0, final_upto) carry their final text
+    std::optional<std::string> final_context;                 // last non-empty text among the final chunks (whisper.rs:175-180)
+    int window = cnt;
+    while (final_upto < cnt) {
+        // ---- speculate: the context of chunk k is the last non-empty text before it, as far as currently known (a chunk that was
+        // never decoded counts as empty; a transcript made with a context that has since changed is still the best guess there is)
+        const int hi = std::min(cnt, final_upto + std::max(1, window));
+        std::vector<int> todo;
+        std::vector<std::optional<std::string>> guess(cnt);
+        {
+            std::optional<std::string> c = final_context;
+            for (int k = final_upto; k < hi; ++k) {
+                guess[k] = c;                                          // chunk final_upto always gets its true context: every round confirms it
+                if (status[k] < 0 || used[k] != c) todo.push_back(k);
+                if (status[k] == 0 && !text[k].empty()) c = text[k];
+            }
+        }
+        if (!todo.empty()) {
+            std::vector<const float*> a;
+            std::vector<int> ns;
+            std::vector<std::optional<std::string>> ctxs;
+            for (int k : todo) { a.push_back(chunks[k]); ns.push_back(n[k]); ctxs.push_back(guess[k]); }
+            std::vector<std::string> texts;
+            std::vector<int> rc;
+            const WhisperError e = transcribe_batch_contexts(a, ns, language, vocabulary, ctxs, texts, &rc);
+            if (e.kind != WhisperError::None) return e;
+            cs.n_rounds += 1;
+            cs.n_decodes += (int)todo.size();
+            for (size_t i = 0; i < todo.size(); ++i) {
+                const int k = todo[i];
+                used[k] = guess[k];
+                status[k] = rc[i] == 0 ? 0 : 1;
+                text[k] = rc[i] == 0 ? texts[i] : std::string();
+                if (rc[i] != 0) err_text[k] = "whisper_full_with_state returned " + std::to_string(rc[i]) + ": " + whisper_b200_last_error();
+            }
+        }
+        // ---- accept the longest prefix whose context was right
+        int confirmed = 0;
+        while (final_upto < cnt && status[final_upto] >= 0 && used[final_upto] == final_context) {
+            const int k = final_upto;
+            if (status[k] > 0 && abort_on_error) return WhisperError{WhisperError::TranscriptionError, err_text[k]};
+            if (status[k] == 0 && !text[k].empty()) final_context = text[k];
+            ++final_upto;
+            ++confirmed;
+        }
+        if (confirmed <= 1) window = std::max(1, window / 2);        // speculation past the first chunk was wasted: narrow it (1 = sequential)
+        else window = std::min(cnt, window * 2);
+    }
+    std::vector<std::string> results;
+    for (int k = 0; k < cnt; ++k) if (status[k] == 0 && !text[k].empty()) results.push_back(text[k]);
+    for (size_t i = 0; i < results.size(); ++i) {
+        if (i) out += " ";
+        out += results[i];
+    }
+    if (stats) *stats = cs;
     return WhisperError{};
 }
 
@@ -356,9 +483,21 @@ int nobs_engine_transcribe_chunked(struct nobs_engine* e, const float* const* ch
 }
 int nobs_engine_transcribe_recording(struct nobs_engine* e, const float* audio, size_t n, const char* language, const char* vocabulary, int parallel,
                                      const char** out) {
-    const nobs::WhisperError err = e->engine.transcribe_recording(audio, n, opt(language), opt(vocabulary), parallel != 0, e->text);
+    const nobs::WhisperError err = e->engine.transcribe_recording(audio, n, opt(language), opt(vocabulary), parallel, e->text);
     e->last_error = err.to_string();
     if (out) *out = e->text.c_str();
+    return (int)err.kind;
+}
+int nobs_engine_transcribe_chunked_parallel(struct nobs_engine* e, const float* const* chunks, const int* n, int n_chunks, const char* language,
+                                            const char* vocabulary, int abort_on_error, const char** out, int* n_decodes, int* n_rounds) {
+    std::vector<const float*> a(chunks, chunks + n_chunks);
+    std::vector<int> ns(n, n + n_chunks);
+    nobs::WhisperEngine::ChainStats cs;
+    const nobs::WhisperError err = e->engine.transcribe_chunked_parallel(a, ns, opt(language), opt(vocabulary), abort_on_error != 0, e->text, &cs);
+    e->last_error = err.to_string();
+    if (out) *out = e->text.c_str();
+    if (n_decodes) *n_decodes = cs.n_decodes;
+    if (n_rounds) *n_rounds = cs.n_rounds;
     return (int)err.kind;
 }
 int nobs_engine_transcribe_batch(struct nobs_engine* e, const float* const* audios, const int* n, int n_audios, const char* language,

@@ -40,18 +40,30 @@ public:
     // whisper.rs:152-197: sequential, previous non-empty text becomes the next chunk's context
     WhisperError transcribe_chunked(const std::vector<std::vector<float>>& chunks, const std::optional<std::string>& language,
                                     const std::optional<std::string>& vocabulary, std::string& out) const;
+    // SURVEY.md §8f N4 — the same result as transcribe_chunked, with the chunks decoded data-parallel.  Chunk k's prompt needs the
+    // text of the last non-empty chunk before it, which is only known once those chunks are decoded; so: decode a window of chunks
+    // together, each with the context known so far (speculation), accept the longest prefix whose context turned out to be right,
+    // re-decode the rest; the window halves when a round only confirmed one chunk and doubles when it confirmed all (window 1 is
+    // exactly the sequential algorithm).  abort_on_error: whisper.rs:182-185 (true) or state.rs:773-775 (false: skip the chunk).
+    struct ChainStats { int n_decodes = 0, n_rounds = 0; };
+    WhisperError transcribe_chunked_parallel(const std::vector<const float*>& chunks, const std::vector<int>& n, const std::optional<std::string>& language,
+                                             const std::optional<std::string>& vocabulary, bool abort_on_error, std::string& out, ChainStats* stats = nullptr) const;
     // B200 addition: independent windows decoded together, no context chaining.
     // beam_size > 0 selects BeamSearch{beam_size, patience:-1}, otherwise Greedy{best_of:1}.
     WhisperError transcribe_batch(const std::vector<const float*>& audios, const std::vector<int>& n, const std::optional<std::string>& language,
                                   const std::optional<std::string>& vocabulary, int beam_size, std::vector<std::string>& out) const;
+    // one context per audio (nullopt: none); per-audio return codes instead of failing the whole batch when rc_out is given
+    WhisperError transcribe_batch_contexts(const std::vector<const float*>& audios, const std::vector<int>& n, const std::optional<std::string>& language,
+                                           const std::optional<std::string>& vocabulary, const std::vector<std::optional<std::string>>& contexts,
+                                           std::vector<std::string>& out, std::vector<int>* rc_out) const;
 
     // state.rs:757-792: what the reference does with the audio left in the buffer when a recording stops — longer
     // than 30 s: cut at silences (audio.rs find_silence_boundaries + split_at_silences), then transcribe the pieces
     // in order, each with the previous non-empty text as context; a failing piece is skipped (state.rs:773-775),
-    // results are joined with " " and trimmed.  parallel == true decodes the pieces together instead (data-parallel,
-    // no context chaining).
+    // results are joined with " " and trimmed.  parallel: 0 sequential (the reference's loop), 1 the pieces together without
+    // context chaining, 2 together WITH the reference's chaining (transcribe_chunked_parallel: same text as 0).
     WhisperError transcribe_recording(const float* audio, size_t n, const std::optional<std::string>& language,
-                                      const std::optional<std::string>& vocabulary, bool parallel, std::string& out) const;
+                                      const std::optional<std::string>& vocabulary, int parallel, std::string& out) const;
 
     whisper_context* raw_context() const { return ctx_; }
     // counters of the last transcribe / transcribe_batch call, summed over its audios

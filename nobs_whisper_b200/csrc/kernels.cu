@@ -3,6 +3,8 @@
 // logit filter / log-softmax / argmax / sampling / top-k kernel.
 // The tcgen05 (tensor-core) kernels live in gemm_sm100.cu / attention_sm100.cu.
 #include "kernels.cuh"
+#include <cooperative_groups.h>
+
 #include "device_utils.cuh"
 
 #include <atomic>
@@ -669,8 +671,13 @@ constexpr int SA_WARPS = 2;   // 128 rows x 20 heads x 64 threads at <= 64 regis
 // partial sums of the QKV projection; the block finishes them (fixed split order, + bias), appends k / v to the cache
 // panel and attends over keys 0..pos with the new row taken from shared memory — the projection's epilogue launch is
 // gone from the latency chain.  Only valid when no two rows of the batch share a KV slot (single-token steps).
-template <typename T>
-__global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
+// PRE (single-token steps of a lane with <= 64 rows: half as many blocks per SM, twice the registers): the first trip of keys AND of
+// values — the cache rows of earlier steps, which do not depend on the predecessor kernel — is requested BEFORE the programmatic
+// dependency wait, so that after the wait only the partial-sum round trip stands between the block and its dot products.  This
+// kernel sits on the latency chain of every decoder layer (profiles/README.md: 23 us per layer before, of which ~10 us were this
+// block's eight dependent memory round trips).
+template <typename T, int MINB, bool PRE>
+__global__ void __launch_bounds__(SA_WARPS * 32, MINB) dec_self_attention_kernel(const RowDesc* __restrict__ rows, const T* __restrict__ q, int ldq,
                                                                           T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
                                                                           int ldo, int n_head, size_t slot_stride, size_t head_stride, QkvPartials qp) {
     constexpr int VN = Vec16<T>::N, LPK = 64 / VN, KPW = 32 / LPK, KPB = KPW * SA_WARPS, UNR = 8;
@@ -681,18 +688,33 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(c
     __shared__ __align__(16) T k_new[64];
     __shared__ __align__(16) T v_new[64];
     const long long tr = trace_begin(3, out);
-    pdl_wait();
-    pdl_launch_dependents();
-    trace_end(trace_begin(103, out));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int r = blockIdx.x, h = blockIdx.y;
-    const RowDesc rd = rows[r];
+    const RowDesc rd = rows[r];   // uploaded before the round's first kernel: safe to read ahead of the dependency wait
     const int nk = min(rd.pos + 1, 448);
     const size_t base = (size_t)rd.kv_slot * slot_stride + (size_t)h * head_stride;
     T* K = kc + base;
     T* V = vc + base;
     const bool fused = qp.partial != nullptr;
     const int j_new = fused ? nk - 1 : -1;    // the key row that only exists in shared memory so far
+    const int sub = lane % LPK, ks = warp * KPW + lane / LPK;   // key slot of this thread within a block iteration
+    constexpr int UNRV = 2;   // values: a quarter of a trip ahead (registers: 80 per thread keep 8 blocks of this kernel beside another lane's attention CTAs)
+    typename Vec16<T>::Raw pre_k[PRE ? UNR : 1], pre_v[PRE ? UNRV : 1];
+    if (PRE) {   // only used with fused == true: rows 0 .. nk-2 were written by earlier rounds
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = u * KPB + ks;
+            pre_k[u] = j < nk - 1 ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < UNRV; ++u) {
+            const int j = u * KPB + ks;
+            pre_v[u] = j < nk - 1 ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
+        }
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    trace_end(trace_begin(103, out));
     if (fused) {
         const int d = n_head * 64;
         for (int e = tid; e < 64; e += SA_WARPS * 32) {   // element e of q, k and v: all split-K loads of a trip in flight together
@@ -712,7 +734,9 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(c
                 for (int u = 0; u < 4; ++u) { aq += tq[u]; ak += tk[u]; av += tv[u]; }   // fixed split order
             }
             if (qp.bias) { aq += __ldg(qp.bias + h * 64 + e); ak += __ldg(qp.bias + d + h * 64 + e); av += __ldg(qp.bias + 2 * d + h * 64 + e); }
-            qs[e] = aq;
+            // q goes through the storage type exactly as on the path that materialises the projection (rounds that contain a
+            // prefill take that path for every row): a row's result must not depend on what else is in its batch
+            qs[e] = to_f32(from_f32<T>(aq));
             const T kb = from_f32<T>(ak), vb = from_f32<T>(av);
             k_new[e] = kb;
             v_new[e] = vb;
@@ -723,7 +747,6 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(c
         for (int e = tid; e < 64; e += SA_WARPS * 32) qs[e] = to_f32(q[(size_t)r * ldq + h * 64 + e]);
     }
     __syncthreads();
-    const int sub = lane % LPK, ks = warp * KPW + lane / LPK;   // key slot of this thread within a block iteration
     float qv[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) qv[i] = qs[sub * VN + i];
@@ -734,6 +757,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(c
         for (int u = 0; u < UNR; ++u) {
             const int j = j0 + u * KPB + ks;
             if (j == j_new) raw[u] = *reinterpret_cast<const typename Vec16<T>::Raw*>(k_new + sub * VN);
+            else if (PRE && j0 == 0) raw[u] = pre_k[u];
             else raw[u] = j < nk ? Vec16<T>::load(K + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
@@ -781,6 +805,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32, 18) dec_self_attention_kernel(c
         for (int u = 0; u < UNR; ++u) {
             const int j = j0 + u * KPB + ks;
             if (j == j_new) raw[u] = *reinterpret_cast<const typename Vec16<T>::Raw*>(v_new + sub * VN);
+            else if (PRE && j0 == 0 && u < UNRV) raw[u] = pre_v[u < UNRV ? u : 0];
             else raw[u] = j < nk ? Vec16<T>::load(V + (size_t)j * 64 + sub * VN) : Vec16<T>::zero();
         }
 #pragma unroll
@@ -819,8 +844,13 @@ void launch_dec_attention(const RowDesc* rows, int n_rows, const T* q, int ldq, 
     if (!cross) {
         dim3 grid(n_rows, n_head);
         const QkvPartials qp = qkv_partials ? *qkv_partials : QkvPartials{};
-        launch_kernel(dec_self_attention_kernel<T>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, const_cast<T*>(kbase), const_cast<T*>(vbase), out, ldo,
-                      n_head, slot_stride, head_stride, qp);
+        static const bool pre_ok = [] { const char* v = getenv("NOBS_WHISPER_SA_PREFETCH"); return !(v && *v == '0'); }();
+        if (pre_ok && qp.partial && sizeof(T) == 2 && n_rows * n_head <= 8 * 148)   // one wave at 8 blocks per SM
+            launch_kernel(dec_self_attention_kernel<T, 12, true>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, const_cast<T*>(kbase), const_cast<T*>(vbase),
+                          out, ldo, n_head, slot_stride, head_stride, qp);
+        else
+            launch_kernel(dec_self_attention_kernel<T, 18, false>, grid, dim3(SA_WARPS * 32), 0, s, true, rows, q, ldq, const_cast<T*>(kbase), const_cast<T*>(vbase),
+                          out, ldo, n_head, slot_stride, head_stride, qp);
         NOBS_COUNT_LAUNCH();
         return;
     }
@@ -1178,10 +1208,287 @@ __global__ void __launch_bounds__(PL_THREADS) process_logits_kernel(const float*
     trace_end(tr);
 }
 
+// ------------------------------------------------------------------------------------------
+// K6 over a thread-block cluster: the same passes as process_logits_kernel, with one row spread over PLC_CL CTAs (contiguous
+// vocabulary ranges) and every block-wide reduction finished through distributed shared memory — each CTA publishes its partial
+// into a slot of every peer's shared memory, one cluster barrier (~0.2 us) per exchange, partials combined in rank order
+// (deterministic).  One row per 1024-thread block made K6 150-220 us of every decoder round (one SM streaming 207 KB five times);
+// eight CTAs per row bring the whole vocabulary pass onto 8 x rows SMs.
+constexpr int PLC_CL = 8;
+constexpr int PLC_THREADS = 512;
+
+__global__ void __cluster_dims__(PLC_CL, 1, 1) __launch_bounds__(PLC_THREADS)
+process_logits_cluster_kernel(const float* __restrict__ logits, int ld, const SampleParams* __restrict__ params, SampleResult* __restrict__ results, VocabIds v,
+                              float* __restrict__ logprobs_out, float* __restrict__ probs_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float red_f[32];
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ double scan_d[32];
+    __shared__ int s_pick;
+    __shared__ int s_chosen[kMaxTopK];
+    // exchange slots, written by the peers: [exchange][source rank][value]
+    __shared__ float xf[5 + kMaxTopK][PLC_CL][2];
+    __shared__ double xd[3][PLC_CL];
+    __shared__ int xi[2 + kMaxTopK][PLC_CL][2];
+
+    const long long tr = trace_begin(7, logits);
+    pdl_wait();
+    pdl_launch_dependents();
+    trace_end(trace_begin(107, logits));
+    const int rank = (int)cluster.block_rank();
+    const int row = blockIdx.y, tid = threadIdx.x;
+    const SampleParams p = params[row];
+    const SuppressCtx sc = make_suppress_ctx(p, v);
+    const float* lg = logits + (size_t)row * ld;
+    const int n = v.n_vocab;
+    const int span = (n + PLC_CL - 1) / PLC_CL;
+    const int lo = rank * span, hi = min(n, lo + span);     // this CTA's vocabulary range
+    const bool scaled = p.temperature > 0.0f;
+    const float* pr_cache = probs_out ? probs_out + (size_t)row * n : nullptr;
+
+    auto put_f = [&](int x, float a, float b) {             // block-uniform a, b -> slot [x][rank] of every CTA of the cluster
+        if (tid < PLC_CL) {
+            float* dst = cluster.map_shared_rank(&xf[x][0][0], tid);
+            dst[rank * 2] = a; dst[rank * 2 + 1] = b;
+        }
+    };
+    auto put_d = [&](int x, double a) {
+        if (tid < PLC_CL) cluster.map_shared_rank(&xd[x][0], tid)[rank] = a;
+    };
+    auto put_i = [&](int x, int a, int b) {
+        if (tid < PLC_CL) {
+            int* dst = cluster.map_shared_rank(&xi[x][0][0], tid);
+            dst[rank * 2] = a; dst[rank * 2 + 1] = b;
+        }
+    };
+
+    // pass A: maxima
+    float lmax = -INFINITY, rawmax = -INFINITY;
+    for (int i = lo + tid; i < hi; i += PLC_THREADS) {
+        const float raw = lg[i];
+        rawmax = fmaxf(rawmax, raw);
+        if (!token_suppressed(i, sc, v)) lmax = fmaxf(lmax, scaled ? __fdiv_rn(raw, p.temperature) : raw);
+    }
+    lmax = block_reduce(lmax, -INFINITY, OpMax(), red_f);
+    rawmax = block_reduce(rawmax, -INFINITY, OpMax(), red_f);
+    put_f(0, lmax, rawmax);
+    cluster.sync();
+    lmax = -INFINITY; rawmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) { lmax = fmaxf(lmax, xf[0][c][0]); rawmax = fmaxf(rawmax, xf[0][c][1]); }
+    // pass B: sums
+    float lsum = 0.0f, rawsum = 0.0f;
+    for (int i = lo + tid; i < hi; i += PLC_THREADS) {
+        const float raw = lg[i];
+        if (p.want_nosp) rawsum += expf(raw - rawmax);
+        if (!token_suppressed(i, sc, v)) lsum += expf((scaled ? __fdiv_rn(raw, p.temperature) : raw) - lmax);
+    }
+    lsum = block_reduce(lsum, 0.0f, OpAddF(), red_f);
+    rawsum = block_reduce(rawsum, 0.0f, OpAddF(), red_f);
+    put_f(1, lsum, rawsum);
+    cluster.sync();
+    lsum = 0.0f; rawsum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) { lsum += xf[1][c][0]; rawsum += xf[1][c][1]; }   // rank order: deterministic
+    const float logsumexp = logf(lsum) + lmax;
+    auto logprob_of = [&](int i) -> float {
+        if (token_suppressed(i, sc, v)) return -INFINITY;
+        const float l = scaled ? __fdiv_rn(lg[i], p.temperature) : lg[i];
+        return l - logsumexp;
+    };
+    // pass C: timestamp logsumexp vs best text token
+    float ts_max = -INFINITY, text_max = -INFINITY;
+    for (int i = lo + tid; i < hi; i += PLC_THREADS) {
+        const float lp = logprob_of(i);
+        if (i >= v.beg) ts_max = fmaxf(ts_max, lp); else text_max = fmaxf(text_max, lp);
+    }
+    ts_max = block_reduce(ts_max, -INFINITY, OpMax(), red_f);
+    text_max = block_reduce(text_max, -INFINITY, OpMax(), red_f);
+    put_f(2, ts_max, text_max);
+    cluster.sync();
+    ts_max = -INFINITY; text_max = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) { ts_max = fmaxf(ts_max, xf[2][c][0]); text_max = fmaxf(text_max, xf[2][c][1]); }
+    float ts_sum = 0.0f;
+    for (int i = max(lo, v.beg) + tid; i < hi; i += PLC_THREADS) {
+        const float lp = logprob_of(i);
+        if (lp > -INFINITY) ts_sum += expf(lp - ts_max);
+    }
+    ts_sum = block_reduce(ts_sum, 0.0f, OpAddF(), red_f);
+    put_f(3, ts_sum, 0.0f);
+    cluster.sync();
+    ts_sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) ts_sum += xf[3][c][0];
+    const float ts_logprob = ts_sum > 0.0f ? logf(ts_sum) + ts_max : -INFINITY;
+    const bool text_off = ts_logprob > text_max;
+    auto final_logprob = [&](int i) -> float {
+        if (text_off && i < v.beg) return -INFINITY;
+        return logprob_of(i);
+    };
+
+    // pass D: probabilities, argmax (first maximum wins), timestamp statistics
+    float best_p = 0.0f; int best_i = INT_MAX;
+    float tsb_p = 0.0f; int tsb_i = INT_MAX;
+    double sum_ts = 0.0;
+    for (int i = lo + tid; i < hi; i += PLC_THREADS) {
+        const float lp = final_logprob(i);
+        const float pr = lp > -INFINITY ? expf(lp) : 0.0f;
+        if (logprobs_out) logprobs_out[(size_t)row * n + i] = lp;
+        if (probs_out) probs_out[(size_t)row * n + i] = pr;
+        if (pr > best_p) { best_p = pr; best_i = i; }
+        if (i >= v.beg) {
+            sum_ts += pr;
+            if (pr > tsb_p) { tsb_p = pr; tsb_i = i; }
+        }
+    }
+    {
+        const float gb = block_reduce(best_p, 0.0f, OpMax(), red_f);
+        int cand = (best_p == gb && best_i != INT_MAX) ? best_i : INT_MAX;
+        const int gbi = block_reduce(cand, INT_MAX, OpMinI(), red_i);
+        const float gt = block_reduce(tsb_p, 0.0f, OpMax(), red_f);
+        cand = (tsb_p == gt && tsb_i != INT_MAX) ? tsb_i : INT_MAX;
+        const int gti = block_reduce(cand, INT_MAX, OpMinI(), red_i);
+        sum_ts = block_reduce(sum_ts, 0.0, OpAddD(), red_d);
+        put_f(4, gb, gt);
+        put_i(0, gbi, gti);
+        put_d(0, sum_ts);
+    }
+    cluster.sync();
+    float gbest_p = 0.0f, gts_p = 0.0f;
+    int gbest_i = INT_MAX, gts_i = INT_MAX;
+    sum_ts = 0.0;
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) { gbest_p = fmaxf(gbest_p, xf[4][c][0]); gts_p = fmaxf(gts_p, xf[4][c][1]); sum_ts += xd[0][c]; }
+#pragma unroll
+    for (int c = 0; c < PLC_CL; ++c) {   // ranges ascend with the rank: the first CTA that holds the maximum holds its lowest index
+        if (xf[4][c][0] == gbest_p && xi[0][c][0] != INT_MAX) gbest_i = min(gbest_i, xi[0][c][0]);
+        if (xf[4][c][1] == gts_p && xi[0][c][1] != INT_MAX) gts_i = min(gts_i, xi[0][c][1]);
+    }
+
+    int pick = gbest_i == INT_MAX ? 0 : gbest_i;
+    if (p.mode == 1) {
+        // inverse-CDF sampling as in process_logits_kernel: q_i = p_i / sum, cp = inclusive prefix sums of q (double), pick = first i
+        // with cp[i] >= u; threads own contiguous chunks of this CTA's range, CTAs contiguous ranges of the vocabulary
+        const int len = max(hi - lo, 0);
+        const int chunk = (len + PLC_THREADS - 1) / PLC_THREADS;
+        const int i0 = lo + tid * chunk, i1 = min(hi, i0 + chunk);
+        auto prob_of = [&](int i) -> double {
+            if (pr_cache) return (double)__ldcg(pr_cache + i);
+            const float lp = final_logprob(i);
+            return lp > -INFINITY ? (double)expf(lp) : 0.0;
+        };
+        double tot = 0.0;
+        for (int i = i0; i < i1; ++i) tot += prob_of(i);
+        tot = block_reduce(tot, 0.0, OpAddD(), red_d);
+        put_d(1, tot);
+        cluster.sync();
+        double total = 0.0;
+#pragma unroll
+        for (int c = 0; c < PLC_CL; ++c) total += xd[1][c];
+        double local = 0.0;
+        for (int i = i0; i < i1; ++i) local += prob_of(i) / total;
+        const int lane = tid & 31, warp = tid >> 5;
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) scan_d[warp] = incl;
+        if (tid == 0) s_pick = INT_MAX;
+        __syncthreads();
+        double woff = 0.0, cta_sum = 0.0;
+        for (int w = 0; w < PLC_THREADS / 32; ++w) { if (w < warp) woff += scan_d[w]; cta_sum += scan_d[w]; }
+        put_d(2, cta_sum);
+        cluster.sync();
+        double cta_off = 0.0;
+        for (int c = 0; c < rank; ++c) cta_off += xd[2][c];
+        double cp = cta_off + woff + incl - local;
+        int found = INT_MAX;
+        if (!(cp >= p.u)) {
+            for (int i = i0; i < i1; ++i) {
+                cp += prob_of(i) / total;
+                if (cp >= p.u) { found = i; break; }
+            }
+        }
+        if (found != INT_MAX) atomicMin(&s_pick, found);
+        __syncthreads();
+        put_i(1, s_pick, 0);
+        cluster.sync();
+        int g = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < PLC_CL; ++c) g = min(g, xi[1][c][0]);
+        pick = g == INT_MAX ? n - 1 : g;   // cp.back() is forced to 1.0 by the reference distribution
+    }
+
+    int n_topk = 0;
+    if (p.mode == 2) {
+        const int k = min(p.k, kMaxTopK);
+        for (int round = 0; round < k; ++round) {
+            float bl = -INFINITY; int bi = INT_MAX;
+            for (int i = lo + tid; i < hi; i += PLC_THREADS) {
+                bool taken = false;
+                for (int c = 0; c < round; ++c) taken |= (s_chosen[c] == i);
+                if (taken) continue;
+                const float lp = final_logprob(i);
+                if (lp > bl) { bl = lp; bi = i; }
+            }
+            const float gl = block_reduce(bl, -INFINITY, OpMax(), red_f);
+            const int c2 = (bl == gl && bi != INT_MAX && gl > -INFINITY) ? bi : INT_MAX;
+            const int gi = block_reduce(c2, INT_MAX, OpMinI(), red_i);
+            put_f(5 + round, gl, 0.0f);
+            put_i(2 + round, gi, 0);
+            cluster.sync();
+            float cl = -INFINITY; int ci = INT_MAX;
+#pragma unroll
+            for (int c = 0; c < PLC_CL; ++c) cl = fmaxf(cl, xf[5 + round][c][0]);
+#pragma unroll
+            for (int c = 0; c < PLC_CL; ++c)
+                if (xf[5 + round][c][0] == cl && xi[2 + round][c][0] != INT_MAX) ci = min(ci, xi[2 + round][c][0]);
+            if (ci == INT_MAX || !(cl > -INFINITY)) break;   // uniform across the cluster
+            if (tid == 0) s_chosen[round] = ci;
+            __syncthreads();
+            n_topk = round + 1;
+        }
+    }
+
+    if (rank == 0 && tid == 0) {
+        SampleResult r;
+        r.id = pick;
+        const float lp = final_logprob(pick);
+        r.plog = lp;
+        r.p = lp > -INFINITY ? expf(lp) : 0.0f;
+        r.tid = gts_i == INT_MAX ? -1 : gts_i;
+        r.pt = (float)((double)gts_p / (sum_ts + 1e-10));
+        r.ptsum = (float)sum_ts;
+        if (pick >= v.beg) { r.tid = pick; r.pt = r.p; }
+        r.no_speech_prob = p.want_nosp ? expf(lg[v.nosp] - (logf(rawsum) + rawmax)) : 0.0f;
+        r.n_topk = n_topk;
+        for (int c = 0; c < kMaxTopK; ++c) {
+            if (c < n_topk) {
+                const int id = s_chosen[c];
+                const float l2 = final_logprob(id);
+                r.topk_id[c] = id; r.topk_plog[c] = l2; r.topk_p[c] = expf(l2);
+            } else { r.topk_id[c] = -1; r.topk_plog[c] = -INFINITY; r.topk_p[c] = 0.0f; }
+        }
+        results[row] = r;
+    }
+    cluster.sync();   // no CTA leaves while a peer may still write into its shared memory
+    trace_end(tr);
+}
+
 void launch_process_logits(const float* logits, int ld, const SampleParams* params, SampleResult* results, int n_rows, const VocabIds& v,
                            float* logprobs_out, float* probs_out, cudaStream_t s) {
     if (n_rows <= 0) return;
-    launch_kernel(process_logits_kernel, dim3(n_rows), dim3(PL_THREADS), 0, s, true, logits, ld, params, results, v, logprobs_out, probs_out);
+    static const bool use_cluster = [] { const char* e = getenv("NOBS_WHISPER_K6_CLUSTER"); return !(e && *e == '0'); }();
+    if (use_cluster)   // one row per cluster of PLC_CL CTAs (the cluster shape is a compile-time attribute of the kernel)
+        launch_kernel(process_logits_cluster_kernel, dim3(PLC_CL, n_rows), dim3(PLC_THREADS), 0, s, true, logits, ld, params, results, v, logprobs_out, probs_out);
+    else
+        launch_kernel(process_logits_kernel, dim3(n_rows), dim3(PL_THREADS), 0, s, true, logits, ld, params, results, v, logprobs_out, probs_out);
     NOBS_COUNT_LAUNCH();
 }
 

@@ -1,7 +1,7 @@
 // Sample-rate conversion to Whisper's 16 kHz (reference src-tauri/src/audio.rs:509-563 `resample_audio`, :329-334
 // `resample_chunk`) — the step right before the transcription path on every recording.
 //
-// The reference calls rubato 0.16 `FftFixedIn::<f32>::new(from, to, 1024, 2, 1)` with 1024-frame chunks (the last
+// The reference calls rubato 0.15.0 (src-tauri/Cargo.lock:3896-3898) `FftFixedIn::<f32>::new(from, to, 1024, 2, 1)` with 1024-frame chunks (the last
 // one zero-padded) and truncates to floor(n * to / from).  rubato is not vendored in the reference tree, so the
 // algorithm below restates the crate's published design (PARITY UNPINNED beyond the reference's own length test,
 // audio.rs:570-583; the CPU oracle oracle/audio_oracle.py::resample_audio restates the same design with numpy FFTs):

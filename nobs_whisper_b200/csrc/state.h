@@ -13,6 +13,8 @@ struct whisper_context {
     nobs::HostModel model;  // tensors are dropped after upload; hparams / vocab / filters stay
     std::unique_ptr<nobs::Engine> engine;
     whisper_context_params params{};
+    whisper_b200_logits_hook logits_hook = nullptr;   // scripted-logits test hook (whisper_b200_set_logits_hook)
+    void* logits_hook_user = nullptr;
 };
 
 namespace nobs {
@@ -45,6 +47,6 @@ namespace nobs {
 void set_last_error(const std::string& e);
 // the batched `full` driver (full.cpp)
 int full_batch(whisper_context* ctx, whisper_state* const* states, int n, const whisper_full_params& params, const float* const* samples,
-               const int* n_samples, int* rc);
+               const int* n_samples, int* rc, const char* const* initial_prompts = nullptr);
 bool ensure_state_slots(whisper_context* ctx, whisper_state* st, int n_kv);
 }  // namespace nobs

@@ -81,9 +81,26 @@ class WhisperEngine:
             self._raise(k)
         return (out.value or b"").decode("utf-8", errors="replace")
 
-    def transcribe_recording(self, audio, language=None, vocabulary=None, parallel: bool = False) -> str:  # state.rs:757-792
+    def transcribe_chunked_parallel(self, chunks, language=None, vocabulary=None, abort_on_error: bool = True):
+        """whisper.rs:152-197 decoded data-parallel: the same text as transcribe_chunked — every chunk's prompt carries
+        the previous non-empty chunk's text — reached by speculative batches.  Returns (text, n_decodes, n_rounds)."""
+        arrs = [np.ascontiguousarray(c, dtype=np.float32) for c in chunks]
+        n = len(arrs)
+        ptrs = (C.POINTER(C.c_float) * max(n, 1))(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+        ns = (C.c_int * max(n, 1))(*[int(a.size) for a in arrs])
+        out = C.c_char_p()
+        nd, nr = C.c_int(0), C.c_int(0)
+        k = self._L.nobs_engine_transcribe_chunked_parallel(self._h, ptrs, ns, n, self._s(language), self._s(vocabulary), int(abort_on_error),
+                                                            C.byref(out), C.byref(nd), C.byref(nr))
+        if k:
+            self._raise(k)
+        return (out.value or b"").decode("utf-8", errors="replace"), nd.value, nr.value
+
+    def transcribe_recording(self, audio, language=None, vocabulary=None, parallel=False) -> str:  # state.rs:757-792
         """The audio left when a recording stops: longer than 30 s it is cut at silences (audio.rs) and the pieces
-        are transcribed in order with the previous text as context (parallel=True: together, no chaining)."""
+        are transcribed in order with the previous text as context (parallel=True / 1: together, no chaining; parallel=2 or "chained":
+        together WITH the chaining, same text as the sequential loop)."""
+        parallel = 2 if parallel == "chained" else int(parallel)
         a = np.ascontiguousarray(audio, dtype=np.float32)
         out = C.c_char_p()
         k = self._L.nobs_engine_transcribe_recording(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), int(a.size), self._s(language),

@@ -203,7 +203,7 @@ class AudioBuffer:
 
 
 # ------------------------------------------------------------------------------------------------------
-# Resampler: reference audio.rs:509-563 `resample_audio` = rubato 0.16
+# Resampler: reference audio.rs:509-563 `resample_audio` = rubato 0.15.0 (src-tauri/Cargo.lock:3896-3898)
 # `FftFixedIn::<f32>::new(from, to, 1024, 2, 1)` fed 1024-frame chunks (last one zero-padded), output truncated to
 # floor(n * to / from).  rubato is NOT vendored in /root/reference (Cargo.lock only), so this is a restatement of
 # its published algorithm from the crate's documented design — PARITY UNPINNED beyond the reference's own test

@@ -63,6 +63,9 @@ def reference_params(language: str | None = "en", initial_prompt: str | None = N
     return p
 
 
+# int hook(user, seek, i_temp, step, decoder, n_prompt, n_vocab, logits*): scripted-logits hook of the control-flow tests
+LOGITS_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float))
+
 _lib = None
 
 
@@ -108,6 +111,7 @@ def lib():
         L.wo_process_logits.restype = C.c_int
         L.wo_process_logits.argtypes = [vp, C.POINTER(WoParams), ip, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp]
         L.wo_set_logits.argtypes = [vp, fp]
+        L.wo_set_logits_hook.argtypes = [vp, LOGITS_HOOK, vp]
         L.wo_canonical_stream.argtypes = [C.POINTER(C.c_double), C.c_int]
         L.wo_sample_stream.argtypes = [fp, C.c_int, ip, C.c_int]
         _lib = L
@@ -150,6 +154,19 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def set_logits_hook(self, fn):
+        """fn(seek, i_temp, step, decoder, n_prompt, logits: np.ndarray view) -> truthy if it overwrote the logits; None removes the hook."""
+        if fn is None:
+            self._hook = None
+            self.L.wo_set_logits_hook(self.h, C.cast(None, LOGITS_HOOK), None)
+            return
+
+        def tramp(_user, seek, it, step, dec, n_prompt, n_vocab, ptr):
+            return 1 if fn(seek, it, step, dec, n_prompt, np.ctypeslib.as_array(ptr, shape=(n_vocab,))) else 0
+
+        self._hook = LOGITS_HOOK(tramp)     # keep the trampoline alive
+        self.L.wo_set_logits_hook(self.h, self._hook, None)
 
     def set_gelu_erf(self, on: bool):
         self.L.wo_set_gelu_erf(self.h, int(on))

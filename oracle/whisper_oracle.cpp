@@ -522,6 +522,10 @@ struct wo_ctx {
     float no_speech_prob = 0;
     int lang_id = 0;
     std::string err;
+    // scripted-logits hook of the control-flow known-answer tests (tests/test_control_flow_kat.py): called after every decode
+    // whose logits are sampled from; may overwrite them.  step = index of the token about to be sampled (0: from the prompt).
+    int (*logits_hook)(void* user, int seek, int i_temp, int step, int decoder, int n_prompt, int n_vocab, float* logits) = nullptr;
+    void* logits_hook_user = nullptr;
     // stats for the benchmark harness
     long n_encode = 0, n_decode_tokens = 0, n_decode_calls = 0, n_fail_p = 0, n_fail_h = 0;
 };
@@ -1036,6 +1040,7 @@ int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
                 }
                 prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
                 if (wo_decode(c, prompt.data(), (int)prompt.size(), 0, 0) != 0) return -7;
+                if (c->logits_hook) c->logits_hook(c->logits_hook_user, seek, it, 0, 0, (int)prompt.size(), hp.n_vocab, c->logits.data());
                 {
                     // no_speech_prob: softmax of the raw logits at the nosp token
                     const Vec& lg = c->logits;
@@ -1133,6 +1138,7 @@ int wo_full(wo_ctx* c, const wo_params* pp, const float* pcm, int n_samples) {
                         if (d.failed || d.completed) continue;
                         int tk = d.sequence.tokens.back().id;
                         if (wo_decode(c, &tk, 1, n_past, j) != 0) return -8;
+                        if (c->logits_hook) c->logits_hook(c->logits_hook_user, seek, it, i + 1, j, (int)prompt.size(), hp.n_vocab, c->logits.data());
                         process_logits(c, d, p, t_cur);
                     }
                 }
@@ -1229,6 +1235,10 @@ int wo_process_logits(wo_ctx* c, const wo_params* p, const int* hist, int n_hist
     if (logprobs_out) memcpy(logprobs_out, d.logprobs.data(), d.logprobs.size() * 4);
     if (probs_out) memcpy(probs_out, d.probs.data(), d.probs.size() * 4);
     return 0;
+}
+void wo_set_logits_hook(wo_ctx* c, int (*hook)(void*, int, int, int, int, int, int, float*), void* user) {
+    c->logits_hook = hook;
+    c->logits_hook_user = user;
 }
 void wo_set_logits(wo_ctx* c, const float* lg) { c->logits.assign(lg, lg + c->model.hp.n_vocab); }
 // draw `n` doubles exactly as std::discrete_distribution draws them from mt19937(0):

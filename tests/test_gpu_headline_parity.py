@@ -125,12 +125,13 @@ VOCAB = ("Claude Code, Anthropic, Supabase, Vercel, shadcn, tRPC, Drizzle, Zod, 
          "SvelteKit, Nuxt, Astro, Vite, Zustand, TanStack, LangChain, LlamaIndex, Ollama, Cursor, Neovim, Vitest, Playwright, Prisma")
 
 
-def beam_params(nw, temperature_inc):
+def beam_params(nw, temperature_inc, single_segment=False):
     p = nw.FullParams.new(nw.SamplingStrategy.BeamSearch(beam_size=5))
     p.set_language("en")
     p.set_initial_prompt(VOCAB)
     p.set_no_context(False); p.set_suppress_blank(True); p.set_no_speech_thold(0.6); p.set_entropy_thold(2.4); p.set_logprob_thold(-1.0)
     p.set_temperature_inc(temperature_inc)
+    p.set_single_segment(single_segment)
     return p
 
 
@@ -144,16 +145,19 @@ def test_base_beam5_bf16_tokens_rescored_by_the_oracle(model_dir):
     ctx = nw.WhisperContext.new_with_params(path, nw.WhisperContextParameters.default(), precision="bf16")
     pcm = synth_audio.synth_clip(1, 30.0)
     st = ctx.create_state()
-    st.full(beam_params(nw, 0.0), pcm)          # one temperature: the transcript is the beam search's own result
+    # one temperature: the transcript is the beam search's own result; single_segment keeps EVERY token of the sequence in the
+    # one segment (segment splitting drops the second timestamp of each pair), so the whole path can be re-scored
+    st.full(beam_params(nw, 0.0, single_segment=True), pcm)
+    assert st.full_n_segments() >= 1
     toks, plogs = [], []
-    for i in range(st.full_n_segments()):
-        seg = st.get_segment(i)
-        for t in range(seg.n_tokens()):
-            td = seg.token_data(t)
-            toks.append(int(td.id)); plogs.append(float(td.plog))
+    seg = st.get_segment(0)                      # the first window's sequence (a trailing sub-second window may follow)
+    for t in range(seg.n_tokens()):
+        td = seg.token_data(t)
+        toks.append(int(td.id)); plogs.append(float(td.plog))
     assert len(toks) > 0
     orc = oracle.Oracle(path)
     prm = oracle.reference_params("en", initial_prompt=VOCAB, beam_size=5, temperature_inc=0.0)
+    prm.single_segment = 1
     orc.mel(pcm)
     orc.encode(0)
     ptoks = orc.tokenize(VOCAB)

@@ -29,6 +29,10 @@ for i in order:
         print(f"{t/1e3:10.2f}  chain        step {k-110} partials in      tag {int(tag[i]) & 0xffffffff:08x}")
     elif 120 <= k < 130:
         print(f"{t/1e3:10.2f}  chain        step {k-120} reduced          tag {int(tag[i]) & 0xffffffff:08x}")
+    elif 130 <= k < 140:
+        print(f"{t/1e3:10.2f}  chain        step {k-130} block 0 GEMM done tag {int(tag[i]) & 0xffffffff:08x}")
+    elif 140 <= k < 150:
+        print(f"{t/1e3:10.2f}  chain        step {k-140} block 0 rows done tag {int(tag[i]) & 0xffffffff:08x}")
 for k in sorted(set(kid)):
     if k in names:
         m = (kid == k) & (t1 > 0)
