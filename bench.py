@@ -176,14 +176,26 @@ def run_reference(args, rank, world, arch_name):
     n_sample = args.cpu_windows
     audio = make_audio(n_sample, 0)
     prm = oracle.reference_params("en")
+    # One step = n_sample whole windows (the unit of the metric cannot be cut smaller: every window runs the full 1500-frame
+    # encoder and the whole temperature ladder).  A window of large-v3 is ~1 minute of CPU work, so the arm is bounded in TIME:
+    # at most one warm-up step (a CPU needs none beyond touching the weights), then as many of the K requested steps as fit
+    # --ref-budget-s (at least one); the JSON line reports the steps actually timed.
     times = []
-    for it in range(args.warmup + args.steps):
+    t_start = time.perf_counter()
+    n_warm = min(args.warmup, 1)
+    steps_run = 0
+    for it in range(n_warm + args.steps):
         t0 = time.perf_counter()
         for a in audio:
             orc.full(prm, a)
         dt = time.perf_counter() - t0
-        if it >= args.warmup:
+        if it >= n_warm:
             times.append(dt)
+            steps_run += 1
+        if it + 1 >= n_warm + 1 and (time.perf_counter() - t_start) + dt > args.ref_budget_s:
+            break
+    args_steps_requested = args.steps
+    args.steps = steps_run
     total = sum(times)
     value = args.steps * n_sample * WINDOW_S / total
     sample = (f"{n_sample} window(s) of {WINDOW_S:.0f} s per step (of the 120-window workload), oracle port of the whisper-rs CPU path, fp32, "
@@ -193,7 +205,7 @@ def run_reference(args, rank, world, arch_name):
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"whisper {arch_name}, 120 x 30-s windows (1 h synthetic 16 kHz audio), greedy + temperature fallback; CPU arm times a bounded sample",
-                   "windows_per_step": n_sample},
+                   "windows_per_step": n_sample, "steps_requested": args_steps_requested, "warmup_run": n_warm, "time_budget_s": args.ref_budget_s},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,6 +224,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-windows", type=int, default=1, help="bounded sample for the CPU arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: stop starting new timed steps once this much wall time is spent")
     ap.add_argument("--no-cpu-4threads", action="store_true", help="skip the second cpu_baseline pass at the upstream default of 4 threads")
     ap.add_argument("--latency-clips", type=int, default=200, help="5-s utterances for the large-v3-turbo latency figure (0: skip); BASELINE config 5 asks for >= 200")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -342,10 +355,23 @@ def main():
                             "sample": f"first {args.cpu_windows} of the {n_win} windows ({args.cpu_windows * WINDOW_S:.0f} s of audio), oracle port of the "
                                       f"whisper-rs CPU path in fp32 (plain OpenMP-SIMD GEMM loops, not ggml's tuned kernels), {cdt:.1f} s of CPU work"}
             if not args.no_cpu_4threads and cores > 4:
-                # the reference never calls set_n_threads (whisper.rs:88-124): it inherits upstream's n_threads = min(4, hw)
-                cdt4 = cpu_run(4)
-                cpu_baseline["at_4_threads"] = {"value": args.cpu_windows * WINDOW_S / cdt4, "unit": "audio-s/s", "cores": 4,
-                                                "note": "upstream default n_threads = min(4, hw), which the reference inherits", "cpu_s": cdt4}
+                # The reference never calls set_n_threads (whisper.rs:88-124): it inherits upstream's n_threads = min(4, hw).  A second full
+                # pass at 4 threads would add minutes to every run, so the 4-thread / all-core TIME RATIO is measured on the same window
+                # with temperature_inc = 0 (mel + encoder + one decoding pass instead of the whole ladder) and applied to the full figure.
+                prm1 = oracle.reference_params("en", temperature_inc=0.0)
+
+                def one_pass(threads):
+                    oracle.lib().wo_set_threads(threads)
+                    t0 = time.perf_counter()
+                    orc.full(prm1, audio[0])
+                    return time.perf_counter() - t0
+
+                t_all, t_4 = one_pass(cores), one_pass(4)
+                oracle.lib().wo_set_threads(cores)
+                cpu_baseline["at_4_threads"] = {"value": cpu_baseline["value"] * t_all / t_4, "unit": "audio-s/s", "cores": 4,
+                                                "note": "upstream default n_threads = min(4, hw), which the reference inherits; all-core figure scaled by the "
+                                                        "4-thread / all-core time ratio measured on the same window with a single decoding pass",
+                                                "one_pass_s_all_cores": t_all, "one_pass_s_4_threads": t_4}
             orc.close()
         steps = args.steps
         # Dominant kernel of the step: the decoder's cross-attention stream over the cross-KV panels

@@ -78,6 +78,8 @@ def lib():
         L.wo_load.restype = vp; L.wo_load.argtypes = [C.c_char_p]
         L.wo_free.argtypes = [vp]
         L.wo_set_gelu_erf.argtypes = [vp, C.c_int]
+        L.wo_set_ggml_faithful.argtypes = [vp, C.c_int]
+        L.wo_gelu.restype = C.c_float; L.wo_gelu.argtypes = [vp, C.c_float]
         L.wo_set_threads.argtypes = [C.c_int]
         L.wo_max_threads.restype = C.c_int
         L.wo_hparams.argtypes = [vp, ip]
@@ -167,6 +169,14 @@ class Oracle:
 
         self._hook = LOGITS_HOOK(tramp)     # keep the trampoline alive
         self.L.wo_set_logits_hook(self.h, self._hook, None)
+
+    def set_ggml_faithful(self, on: bool):
+        """ggml's CPU roundings on top of the ideal-fp32 graph: f16 mul_mat activations (f16 models), f16 im2col, f16 GELU table,
+        f16 KV caches, f16 attention operands."""
+        self.L.wo_set_ggml_faithful(self.h, int(on))
+
+    def gelu(self, x: float) -> float:
+        return float(self.L.wo_gelu(self.h, float(x)))
 
     def set_gelu_erf(self, on: bool):
         self.L.wo_set_gelu_erf(self.h, int(on))

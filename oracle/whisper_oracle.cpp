@@ -18,8 +18,8 @@
 // The algorithm below restates whisper.cpp's published algorithm (whisper_full_with_state,
 // log_mel_spectrogram, whisper_encode_internal, whisper_decode_internal,
 // whisper_process_logits, whisper_sample_token, whisper_sequence_score, tokenize) as
-// summarised in SURVEY.md §8a rows a1, a4-a11, in "ideal fp32" numerics (no f16 GELU table,
-// no f16 im2col / KV rounding).
+// summarised in SURVEY.md §8a rows a1, a4-a11, in "ideal fp32" numerics by default (no f16 GELU table,
+// no f16 im2col / KV rounding); wo_set_ggml_faithful() switches those roundings on (see wo_ctx::faithful).
 //
 // PARITY UNPINNED: the reference's own tests hold no golden vector for mel / encoder /
 // logits / tokens (only whisper.rs:272-305 pins NoModel + the hallucination
@@ -356,12 +356,28 @@ void layer_norm(const float* x, const float* g, const float* b, float* y, int ro
     }
 }
 
-// whisper.cpp/ggml GELU: tanh approximation (ideal fp32, no f16 table).  "erf" is only used
-// to cross-check against HF transformers (which uses exact GELU).
+// round-to-nearest-even fp32 -> IEEE half -> fp32 (what ggml's GGML_FP32_TO_FP16 / F16C does)
+inline float round_f16(float x) { return (float)(_Float16)x; }
+void round_f16_inplace(float* v, size_t n) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) v[i] = round_f16(v[i]);
+}
+
+// whisper.cpp/ggml GELU: tanh approximation.  Default: ideal fp32 (no f16 table).  "erf" is only used to cross-check against
+// HF transformers (which uses exact GELU).  f16_table: ggml's CPU path as it really runs — ggml_vec_gelu_f32 looks the value
+// up in a table indexed by the HALF-precision bit pattern of x and stored in half precision: y = f16(gelu(f16(x))) for
+// -10 < x < 10, 0 below, x above.
 struct Gelu {
     bool erf_mode = false;
+    bool f16_table = false;
     inline float operator()(float x) const {
         if (erf_mode) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+        if (f16_table) {
+            if (x <= -10.0f) return 0.0f;
+            if (x >= 10.0f) return x;
+            const float xh = round_f16(x);
+            return round_f16(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh))));
+        }
         return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
     }
 };
@@ -522,6 +538,12 @@ struct wo_ctx {
     float no_speech_prob = 0;
     int lang_id = 0;
     std::string err;
+    // "ggml-faithful" numerics (SURVEY.md §7 step 1, §8c hazard 1): the roundings ggml's CPU backend applies on top of the ideal
+    // fp32 graph — (1) mul_mat converts its activation operand to the weight's vec_dot type, i.e. to f16 for f16 weights,
+    // (2) conv1d runs through an f16 im2col, (3) GELU goes through the f16 table, (4) self- and cross-KV are stored in f16, and the
+    // attention products take f16 operands (Q and the softmax probabilities are converted because K / V are f16).
+    // Off by default: the product's tolerances are stated against the ideal-fp32 mode; this mode measures how far apart the two are.
+    bool faithful = false;
     // scripted-logits hook of the control-flow known-answer tests (tests/test_control_flow_kat.py): called after every decode
     // whose logits are sampled from; may overwrite them.  step = index of the token about to be sampled (0: from the prompt).
     int (*logits_hook)(void* user, int seek, int i_temp, int step, int decoder, int n_prompt, int n_vocab, float* logits) = nullptr;
@@ -548,6 +570,8 @@ wo_ctx* wo_load(const char* path) {
 }
 void wo_free(wo_ctx* c) { delete c; }
 void wo_set_gelu_erf(wo_ctx* c, int on) { c->gelu.erf_mode = on != 0; }
+void wo_set_ggml_faithful(wo_ctx* c, int on) { c->faithful = on != 0; c->gelu.f16_table = on != 0; }
+float wo_gelu(wo_ctx* c, float x) { return c->gelu(x); }   // the activation in the context's current numeric mode (known-answer tests)
 void wo_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);
@@ -611,6 +635,10 @@ int wo_encode(wo_ctx* c, int mel_offset) {
                 if (tt >= 0 && tt < T && i0 + tt < i1) v = c->mel.data[(size_t)ch * c->mel.n_len + i0 + tt];
                 A1[((size_t)t * nm + ch) * 3 + k] = v;
             }
+    // faithful mode: F = "this tensor is handed to ggml_mul_mat next to f16 data" -> rounded to f16 first
+    const bool fa = c->faithful, fw = c->faithful && hp.ftype == 1;   // fw: the model's matrices are f16 (ggml-<id>.bin as shipped)
+    auto F = [&](Vec& t, bool on) { if (on) round_f16_inplace(t.data(), t.size()); };
+    F(A1, fa);   // ggml_conv_1d: im2col writes f16
     Vec h1((size_t)T * d);
     gemm_nt(A1.data(), nm * 3, m.e_conv1_w.data(), nm * 3, m.e_conv1_b.data(), h1.data(), d, T, d, nm * 3);
     for (auto& v : h1) v = c->gelu(v);
@@ -623,6 +651,7 @@ int wo_encode(wo_ctx* c, int mel_offset) {
                 int tt = 2 * t + k - 1;
                 A2[((size_t)t * d + ch) * 3 + k] = (tt >= 0 && tt < T) ? h1[(size_t)tt * d + ch] : 0.0f;
             }
+    F(A2, fa);
     Vec x((size_t)n_ctx * d);
     gemm_nt(A2.data(), d * 3, m.e_conv2_w.data(), d * 3, m.e_conv2_b.data(), x.data(), d, n_ctx, d, d * 3);
     for (size_t i = 0; i < x.size(); ++i) x[i] = c->gelu(x[i]) + m.e_pe[i];
@@ -633,9 +662,11 @@ int wo_encode(wo_ctx* c, int mel_offset) {
     const float scale = 1.0f / sqrtf((float)dh);
     for (const Block& b : m.enc) {
         layer_norm(x.data(), b.attn.ln_w.data(), b.attn.ln_b.data(), y.data(), n_ctx, d);
+        F(y, fw);
         gemm_nt(y.data(), d, b.attn.q_w.data(), d, b.attn.q_b.data(), q.data(), d, n_ctx, d, d);
         gemm_nt(y.data(), d, b.attn.k_w.data(), d, nullptr, k.data(), d, n_ctx, d, d);
         gemm_nt(y.data(), d, b.attn.v_w.data(), d, b.attn.v_b.data(), v.data(), d, n_ctx, d, d);
+        F(k, fa); F(v, fa); F(q, fa);   // K and V are copied into f16 tensors; Q is converted because its partner K is f16
         // non-causal attention, one head at a time (threads across query rows)
         for (int h = 0; h < n_head; ++h) {
             Vec vt((size_t)dh * n_ctx);
@@ -652,14 +683,18 @@ int wo_encode(wo_ctx* c, int mel_offset) {
                 for (int j = 0; j < n_ctx; ++j) { r[j] = expf(r[j] - mx); sum += r[j]; }
                 const float inv = (float)(1.0 / sum);
                 for (int j = 0; j < n_ctx; ++j) r[j] *= inv;
+                if (fa) for (int j = 0; j < n_ctx; ++j) r[j] = round_f16(r[j]);   // mul_mat(V f16, softmax): probabilities become f16
             }
             gemm_nt(s.data(), n_ctx, vt.data(), n_ctx, nullptr, att.data() + h * dh, d, n_ctx, dh, n_ctx);
         }
+        F(att, fw);
         gemm_nt(att.data(), d, b.attn.o_w.data(), d, b.attn.o_b.data(), y.data(), d, n_ctx, d, d);
         for (size_t i = 0; i < x.size(); ++i) x[i] += y[i];
         layer_norm(x.data(), b.mlp_ln_w.data(), b.mlp_ln_b.data(), y.data(), n_ctx, d);
+        F(y, fw);
         gemm_nt(y.data(), d, b.fc1_w.data(), d, b.fc1_b.data(), hbuf.data(), 4 * d, n_ctx, 4 * d, d);
         for (auto& t : hbuf) t = c->gelu(t);
+        F(hbuf, fw);
         gemm_nt(hbuf.data(), 4 * d, b.fc2_w.data(), 4 * d, b.fc2_b.data(), y.data(), d, n_ctx, d, 4 * d);
         for (size_t i = 0; i < x.size(); ++i) x[i] += y[i];
     }
@@ -667,11 +702,14 @@ int wo_encode(wo_ctx* c, int mel_offset) {
     layer_norm(x.data(), m.e_ln_w.data(), m.e_ln_b.data(), c->enc_out.data(), n_ctx, d);
     // cross-KV projection per decoder layer (K has no bias)
     const int dt = hp.n_text_state;
+    Vec enc_in = c->enc_out;
+    F(enc_in, fw);
     for (int l = 0; l < hp.n_text_layer; ++l) {
         c->cross_k[l].resize((size_t)n_ctx * dt);
         c->cross_v[l].resize((size_t)n_ctx * dt);
-        gemm_nt(c->enc_out.data(), d, m.dec[l].cross.k_w.data(), d, nullptr, c->cross_k[l].data(), dt, n_ctx, dt, d);
-        gemm_nt(c->enc_out.data(), d, m.dec[l].cross.v_w.data(), d, m.dec[l].cross.v_b.data(), c->cross_v[l].data(), dt, n_ctx, dt, d);
+        gemm_nt(enc_in.data(), d, m.dec[l].cross.k_w.data(), d, nullptr, c->cross_k[l].data(), dt, n_ctx, dt, d);
+        gemm_nt(enc_in.data(), d, m.dec[l].cross.v_w.data(), d, m.dec[l].cross.v_b.data(), c->cross_v[l].data(), dt, n_ctx, dt, d);
+        F(c->cross_k[l], fa); F(c->cross_v[l], fa);   // the cross-KV cache is f16
     }
     return 0;
 }
@@ -690,6 +728,8 @@ int wo_decode(wo_ctx* c, const int* tokens, int n, int n_past, int seq) {
     if (c->enc_out.empty()) return -2;
     c->n_decode_calls++;
     c->n_decode_tokens += n;
+    const bool fa = c->faithful, fw = c->faithful && hp.ftype == 1;   // see wo_encode
+    auto F = [&](Vec& t, bool on) { if (on) round_f16_inplace(t.data(), t.size()); };
     Vec x((size_t)n * d), y((size_t)n * d), q((size_t)n * d), att((size_t)n * d), hbuf((size_t)n * 4 * d), tmp((size_t)n * d);
     for (int i = 0; i < n; ++i)
         for (int e = 0; e < d; ++e) x[(size_t)i * d + e] = m.d_te[(size_t)tokens[i] * d + e] + m.d_pe[(size_t)(n_past + i) * d + e];
@@ -701,9 +741,15 @@ int wo_decode(wo_ctx* c, const int* tokens, int n, int n_past, int seq) {
         if (K.empty()) { K.assign((size_t)hp.n_text_ctx * d, 0.0f); V.assign((size_t)hp.n_text_ctx * d, 0.0f); }
         // self-attention with KV append
         layer_norm(x.data(), b.attn.ln_w.data(), b.attn.ln_b.data(), y.data(), n, d);
+        F(y, fw);
         gemm_nt(y.data(), d, b.attn.q_w.data(), d, b.attn.q_b.data(), q.data(), d, n, d, d);
         gemm_nt(y.data(), d, b.attn.k_w.data(), d, nullptr, K.data() + (size_t)n_past * d, d, n, d, d);
         gemm_nt(y.data(), d, b.attn.v_w.data(), d, b.attn.v_b.data(), V.data() + (size_t)n_past * d, d, n, d, d);
+        if (fa) {   // the self-KV cache is f16; Q is converted next to it
+            round_f16_inplace(K.data() + (size_t)n_past * d, (size_t)n * d);
+            round_f16_inplace(V.data() + (size_t)n_past * d, (size_t)n * d);
+            round_f16_inplace(q.data(), q.size());
+        }
 #pragma omp parallel for collapse(2) schedule(static)
         for (int i = 0; i < n; ++i)
             for (int h = 0; h < n_head; ++h) {
@@ -724,16 +770,19 @@ int wo_decode(wo_ctx* c, const int* tokens, int n, int n_past, int seq) {
                 float* o = att.data() + (size_t)i * d + h * dh;
                 for (int e = 0; e < dh; ++e) o[e] = 0;
                 for (int j = 0; j < nk; ++j) {
-                    const float pj = s[j] * inv;
+                    const float pj = fa ? round_f16(s[j] * inv) : s[j] * inv;
                     const float* vj = V.data() + (size_t)j * d + h * dh;
                     for (int e = 0; e < dh; ++e) o[e] += pj * vj[e];
                 }
             }
+        F(att, fw);
         gemm_nt(att.data(), d, b.attn.o_w.data(), d, b.attn.o_b.data(), tmp.data(), d, n, d, d);
         for (size_t i = 0; i < x.size(); ++i) x[i] += tmp[i];
         // cross-attention over the n_ctx encoder positions
         layer_norm(x.data(), b.cross.ln_w.data(), b.cross.ln_b.data(), y.data(), n, d);
+        F(y, fw);
         gemm_nt(y.data(), d, b.cross.q_w.data(), d, b.cross.q_b.data(), q.data(), d, n, d, d);
+        F(q, fa);
         const Vec& CK = c->cross_k[l];
         const Vec& CV = c->cross_v[l];
 #pragma omp parallel for collapse(2) schedule(static)
@@ -755,22 +804,26 @@ int wo_decode(wo_ctx* c, const int* tokens, int n, int n_past, int seq) {
                 float* o = att.data() + (size_t)i * d + h * dh;
                 for (int e = 0; e < dh; ++e) o[e] = 0;
                 for (int j = 0; j < n_ctx; ++j) {
-                    const float pj = s[j] * inv;
+                    const float pj = fa ? round_f16(s[j] * inv) : s[j] * inv;
                     const float* vj = CV.data() + (size_t)j * d + h * dh;
                     for (int e = 0; e < dh; ++e) o[e] += pj * vj[e];
                 }
             }
+        F(att, fw);
         gemm_nt(att.data(), d, b.cross.o_w.data(), d, b.cross.o_b.data(), tmp.data(), d, n, d, d);
         for (size_t i = 0; i < x.size(); ++i) x[i] += tmp[i];
         // MLP
         layer_norm(x.data(), b.mlp_ln_w.data(), b.mlp_ln_b.data(), y.data(), n, d);
+        F(y, fw);
         gemm_nt(y.data(), d, b.fc1_w.data(), d, b.fc1_b.data(), hbuf.data(), 4 * d, n, 4 * d, d);
         for (auto& t : hbuf) t = c->gelu(t);
+        F(hbuf, fw);
         gemm_nt(hbuf.data(), 4 * d, b.fc2_w.data(), 4 * d, b.fc2_b.data(), tmp.data(), d, n, d, 4 * d);
         for (size_t i = 0; i < x.size(); ++i) x[i] += tmp[i];
     }
     Vec last(d);
     layer_norm(x.data() + (size_t)(n - 1) * d, m.d_ln_w.data(), m.d_ln_b.data(), last.data(), 1, d);
+    F(last, fw);
     c->logits.resize(hp.n_vocab);
     gemm_nt(last.data(), d, m.d_te.data(), d, nullptr, c->logits.data(), hp.n_vocab, 1, hp.n_vocab, d);
     return 0;
