@@ -383,6 +383,12 @@ int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n
 /* Micro-benchmark hook: average device microseconds per launch of the decoder-step kernels for R token
  * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..12]; out_us holds 16 floats). */
 int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, float* out_us);
+/* Fused decoder projection (csrc/decode_proj_sm100.cu) on caller data: out [R][N] = in [R][K] * W[N][K]^T (+ bias, GELU); with resid the
+ * fp32 sum resid + v is returned, with ln_g / ln_b also y_out = LayerNorm(out) (bf16 widened) and the per-tile (mean, M2) workspace
+ * stats_out [N/128][128][2].  iters > 0 also times back-to-back launches. */
+int whisper_b200_debug_dec_proj(int R, int N, int K, const float* in, const float* W, const float* bias, int act, const float* resid,
+                                const float* ln_g, const float* ln_b, float* out, float* y_out, float* stats_out, int iters,
+                                float* us_per_launch);
 /* Micro-benchmark of the device-wide barrier of the fused projection chains: microseconds per barrier over `ctas` CTAs;
  * variant 0 fence + atomic + nanosleep polling, 1 without nanosleep, 2 acq_rel atomic / release increment / acquire polling;
  * store_floats fp32 stores per thread in front of every barrier. */

@@ -228,6 +228,7 @@ SIGNATURES = {
     "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
     "whisper_b200_debug_dec_cross_attention": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, C.c_int]),
     "whisper_b200_debug_time_decode_kernels": (C.c_int, [C.c_int, C.c_int, C.c_int, fp]),
+    "whisper_b200_debug_dec_proj": (C.c_int, [C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int, fp, fp, fp, fp, fp, fp, C.c_int, fp]),
     "whisper_b200_debug_grid_sync": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "whisper_b200_window_rms": (C.c_int, [fp, C.c_size_t, C.c_uint32, fp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nobs_find_silence_boundaries": (C.c_int, [fp, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -245,8 +245,11 @@ __device__ __forceinline__ float tmem_ld_1(uint32_t taddr) {
 // SP: TMEM column pitch between the score blocks of consecutive chunks.  16 = disjoint blocks (256 columns
 // allocated); 4 = overlapping blocks written in increasing order, each MMA's don't-care columns are overwritten by
 // the following chunk's real column (128 columns allocated, two CTAs fit next to the projection GEMMs).
-template <int TC_STAGES, int SP>
-__global__ void __launch_bounds__(192, 1)
+// MINB: minimum resident CTAs per SM the register allocation is sized for.  4 caps the kernel at 80 registers (114 without a cap,
+// no spills either way): two of these CTAs then take 30.7 K of the SM's 64 K registers instead of 46 K, which is what lets the
+// projection kernels of TWO other decode lanes (or a kernel and its programmatic successor) be resident beside them.
+template <int TC_STAGES, int SP, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const RowDesc* __restrict__ rows, int n_items, int n_head,
                               const bf16* __restrict__ q, int ldq, bf16* __restrict__ out, int ldo, long long k_row0, long long v_row0,
                               long long slot_rows, int n_keys, int* __restrict__ sched, CrossQPartials qp) {
@@ -499,19 +502,19 @@ void trace_set_cross(unsigned long long* buf, unsigned int cap) {
 
 namespace {
 int env_or(const char* name, int dflt);
-template <int STAGES, int SP>
+template <int STAGES, int SP, int MINB>
 bool launch_tc(const CUtensorMap& tm, const RowDesc* rows, int n_items, int n_head, const bf16* q, int ldq, bf16* out, int ldo, long long k_row0,
                long long v_row0, long long slot_rows, int n_keys, int* sched, const CrossQPartials& qp, int grid, cudaStream_t s) {
     constexpr int SMEM = tc_smem_bytes(STAGES);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(dec_cross_attention_tc_kernel<STAGES, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(dec_cross_attention_tc_kernel<STAGES, SP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
             sm100_set_error("cudaFuncSetAttribute(cross attention tc smem) failed");
             return false;
         }
         configured = true;
     }
-    launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo, k_row0,
+    launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP, MINB>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo, k_row0,
                   v_row0, slot_rows, n_keys, sched, qp);
     return true;
 }
@@ -527,12 +530,13 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
         sm100_set_error("cross attention (tc): unsupported shape");
         return false;
     }
-    static int sms = 0, stages = 0, sp = 0, per_sm = 1;
+    static int sms = 0, stages = 0, sp = 0, per_sm = 1, low_regs = 1;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        low_regs = env_or("NOBS_WHISPER_CROSS_LOW_REGS", 1);
         stages = env_or("NOBS_WHISPER_CROSS_STAGES", 3);
         sp = env_or("NOBS_WHISPER_CROSS_SPACING", 4);
         per_sm = env_or("NOBS_WHISPER_CROSS_PER_SM", 2);
@@ -549,11 +553,21 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
     const int n_items = n_rows * n_head;
     int grid = n_items < sms * per_sm ? n_items : sms * per_sm;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    // Balanced waves: 1200 items on 296 CTAs are four full waves plus 16 stragglers, and the launch ends one item time (~10 us of a
+    // nearly idle HBM) after most CTAs have run dry.  The stream is bandwidth-bound, so a slightly smaller grid in which every CTA
+    // takes the same number of items (1200 = 240 x 5) finishes with the bandwidth-bound time and no tail.
+    static const int balance = env_or("NOBS_WHISPER_CROSS_BALANCE", 1);
+    if (balance && n_items > grid) {
+        const int waves = (n_items + grid - 1) / grid;
+        grid = (n_items + waves - 1) / waves;
+    }
     bool ok = false;
-#define TC_CASE(S, P) if (stages == S && sp == P) ok = launch_tc<S, P>(tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, qp, grid, s); else
+#define TC_ARGS tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, qp, grid, s
+#define TC_CASE(S, P) if (stages == S && sp == P) ok = low_regs ? launch_tc<S, P, 4>(TC_ARGS) : launch_tc<S, P, 1>(TC_ARGS); else
     TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(2, 4) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
     { sm100_set_error("cross attention (tc): unsupported NOBS_WHISPER_CROSS_STAGES / _SPACING"); return false; }
 #undef TC_CASE
+#undef TC_ARGS
     if (!ok) return false;
     count_launch();
     const cudaError_t err = cudaGetLastError();

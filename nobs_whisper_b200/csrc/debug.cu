@@ -240,6 +240,75 @@ extern "C" int whisper_b200_debug_time_decode_kernels(int R, int d, int iters, f
     return 0;
 }
 
+// Fused decoder projection test hook (decode_proj_sm100.cu).  in fp32 [R][K] (rounded to bf16 on the device), W fp32 [N][K] (rounded
+// to bf16), bias [N] or NULL, act 1 = GELU.  resid fp32 [R][N] or NULL: with it out = resid + v (fp32), otherwise the bf16 result is
+// returned widened.  ln_g / ln_b [N] (needs resid): y_out [R][N] = LayerNorm(out) * g + b, bf16 widened; stats_out [N/128][128][2]
+// receives the per-tile (mean, M2) workspace.  iters > 0: also times back-to-back launches.
+extern "C" int whisper_b200_debug_dec_proj(int R, int N, int K, const float* in, const float* W, const float* bias, int act, const float* resid,
+                                           const float* ln_g, const float* ln_b, float* out, float* y_out, float* stats_out, int iters,
+                                           float* us_per_launch) {
+    if (R <= 0 || R > 128 || !in || !W || !out) return -1;
+    if (!dec_proj_supported(R, N, K)) { set_last_error("debug_dec_proj: unsupported shape"); return -1; }
+    const bool ln = ln_g != nullptr;
+    if (ln && (!resid || !ln_b || !y_out)) return -1;
+    const size_t in_elems = (size_t)R * K, w_elems = (size_t)N * K, o_elems = (size_t)R * N;
+    DevBuf dIn, dInB, dWf, dW, dBias, dX, dG, dB, dSo, dOutB, dOutF, dY, dTicket;
+    if (!dIn.alloc(in_elems * 4) || !dInB.alloc(in_elems * 2) || !dWf.alloc(w_elems * 4) || !dW.alloc(w_elems * 2) || !dBias.alloc((size_t)N * 4) ||
+        !dX.alloc(o_elems * 4) || !dG.alloc((size_t)N * 4) || !dB.alloc((size_t)N * 4) || !dSo.alloc((size_t)40 * 128 * 8) || !dOutB.alloc(o_elems * 2) ||
+        !dOutF.alloc(o_elems * 4) || !dY.alloc(o_elems * 2) || !dTicket.alloc(256))
+        return -2;
+    cudaStream_t s = nullptr;
+    cudaMemcpy(dIn.p, in, in_elems * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dWf.p, W, w_elems * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dTicket.p, 0, 256);
+    cudaMemset(dSo.p, 0, (size_t)40 * 128 * 8);
+    launch_convert<float, bf16>((const float*)dIn.p, (bf16*)dInB.p, in_elems, s);
+    launch_convert<float, bf16>((const float*)dWf.p, (bf16*)dW.p, w_elems, s);
+    ProjDesc p;
+    p.R = R; p.N = N; p.K = K; p.W = (const bf16*)dW.p; p.act = act; p.X = (const bf16*)dInB.p; p.ldx = K;
+    if (bias) { cudaMemcpy(dBias.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice); p.bias = (const float*)dBias.p; }
+    if (resid) p.x = (float*)dX.p; else { p.out = (bf16*)dOutB.p; p.out_ld = N; }
+    if (ln) {
+        cudaMemcpy(dG.p, ln_g, (size_t)N * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB.p, ln_b, (size_t)N * 4, cudaMemcpyHostToDevice);
+        p.y = (bf16*)dY.p; p.ln_g = (const float*)dG.p; p.ln_b = (const float*)dB.p; p.stats_out = (float2*)dSo.p; p.ticket = (int*)dTicket.p;
+    }
+    if (resid) cudaMemcpyAsync(dX.p, resid, o_elems * 4, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(dOutB.p, 0xff, o_elems * 2, s);
+    cudaMemsetAsync(dY.p, 0xff, o_elems * 2, s);
+    if (!launch_dec_proj_sm100(p, s)) { set_last_error(std::string("debug_dec_proj: ") + sm100_last_error()); return -3; }
+    if (resid) cudaMemcpyAsync(out, dX.p, o_elems * 4, cudaMemcpyDeviceToHost, s);
+    else {
+        launch_convert<bf16, float>((const bf16*)dOutB.p, (float*)dOutF.p, o_elems, s);
+        cudaMemcpyAsync(out, dOutF.p, o_elems * 4, cudaMemcpyDeviceToHost, s);
+    }
+    if (ln) {
+        launch_convert<bf16, float>((const bf16*)dY.p, (float*)dOutF.p, o_elems, s);
+        cudaMemcpyAsync(y_out, dOutF.p, o_elems * 4, cudaMemcpyDeviceToHost, s);
+        if (stats_out) cudaMemcpyAsync(stats_out, dSo.p, (size_t)(N / 128) * 128 * 8, cudaMemcpyDeviceToHost, s);
+    }
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) { set_last_error(std::string("debug_dec_proj: ") + cudaGetErrorString(err)); return -4; }
+    int ticket = -1;
+    cudaMemcpy(&ticket, dTicket.p, 4, cudaMemcpyDeviceToHost);
+    if (ticket != 0) { set_last_error("debug_dec_proj: the ticket was not re-armed"); return -5; }
+    if (iters > 0 && us_per_launch) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 3; ++i) launch_dec_proj_sm100(p, s);
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i) launch_dec_proj_sm100(p, s);
+        cudaEventRecord(e1, s);
+        err = cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (err != cudaSuccess) { set_last_error(std::string("debug_dec_proj: ") + cudaGetErrorString(err)); return -4; }
+        *us_per_launch = 1e3f * ms / iters;
+    }
+    return 0;
+}
+
 // Micro-benchmark of the device-wide barrier used by the fused projection chains: `iters` barriers over `ctas` CTAs of 256 threads;
 // before every barrier each thread stores store_floats fp32 values (emulates the partial-sum burst in front of the real barrier).
 namespace {

@@ -17,7 +17,7 @@ namespace nobs {
     do {                                                                                       \
         cudaError_t e_ = (expr);                                                               \
         if (e_ != cudaSuccess) {                                                               \
-            err_ = std::string(#expr) + " failed: " + cudaGetErrorString(e_);                  \
+            set_err(std::string(#expr) + " failed: " + cudaGetErrorString(e_));                \
             return false;                                                                      \
         }                                                                                      \
     } while (0)
@@ -101,7 +101,7 @@ public:
             cudaMemcpy(h.data(), trace_buf_ + 4 + 4 * skip, h.size() * 8, cudaMemcpyDeviceToHost);
             if (FILE* f = fopen(trace_path_.c_str(), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
             fprintf(stderr, "[nobs trace] %llu entries recorded, wrote %llu from %llu to %s\n", n, cnt, skip, trace_path_.c_str());
-            trace_set_kernels(nullptr, 0); trace_set_gemm(nullptr, 0); trace_set_cross(nullptr, 0); trace_set_chain(nullptr, 0);
+            trace_set_kernels(nullptr, 0); trace_set_gemm(nullptr, 0); trace_set_cross(nullptr, 0); trace_set_chain(nullptr, 0); trace_set_proj(nullptr, 0);
             cudaFree(trace_buf_);
         }
         for (auto& e : main_marks_.pool) cudaEventDestroy(e);
@@ -120,11 +120,11 @@ public:
     bool init(const HostModel& hm) {
         int n_dev = 0;
         CUDA_OK(cudaGetDeviceCount(&n_dev));
-        if (device_ < 0 || device_ >= n_dev) { err_ = "invalid CUDA device " + std::to_string(device_); return false; }
+        if (device_ < 0 || device_ >= n_dev) { set_err("invalid CUDA device " + std::to_string(device_)); return false; }
         CUDA_OK(cudaSetDevice(device_));
         cudaDeviceProp prop;
         CUDA_OK(cudaGetDeviceProperties(&prop, device_));
-        if (prop.major != 10) { err_ = std::string("device '") + prop.name + "' is not sm_100 (this library has no other code path)"; return false; }
+        if (prop.major != 10) { set_err(std::string("device '") + prop.name + "' is not sm_100 (this library has no other code path)"); return false; }
         CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) CUDA_OK(cudaEventCreate(&e));
         d_ = hp_.n_audio_state;
@@ -142,6 +142,7 @@ public:
             trace_set_gemm(trace_buf_, trace_cap_);
             trace_set_cross(trace_buf_, trace_cap_);
             trace_set_chain(trace_buf_, trace_cap_);
+            trace_set_proj(trace_buf_, trace_cap_);
         }
         CUDA_OK(cudaStreamSynchronize(stream_));
         return true;
@@ -230,7 +231,10 @@ public:
     }
 
     // ------------------------------------------------------------------ K2-K4
+    // Lanes may be driven by one host thread each (full.cpp): the encoder (one stream, one set of activations) is taken by one
+    // thread at a time, while the other lanes keep decoding.
     bool encode(const std::vector<EncodeRequest>& reqs) override {
+        std::lock_guard<std::mutex> enc_lock(enc_mu_);
         CUDA_OK(cudaSetDevice(device_));
         CUDA_OK(cudaEventRecord(ev_[0], stream_));
         for (size_t b0 = 0; b0 < reqs.size(); b0 += enc_batch_) {
@@ -242,6 +246,7 @@ public:
         CUDA_OK(cudaGetLastError());
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        std::lock_guard<std::mutex> stats_lock(stats_mu_);
         stats.ms_encode += ms;
         collect_marks();
         return true;
@@ -298,7 +303,7 @@ public:
         PackJob* pj = reinterpret_cast<PackJob*>(pin_);
         for (int w = 0; w < nb; ++w) {
             const DeviceMel& m = *reqs[w].mel;
-            if (!m.raw || reqs[w].audio_slot < 0 || reqs[w].audio_slot >= audio_cap_) { err_ = "encode: bad request"; return false; }
+            if (!m.raw || reqs[w].audio_slot < 0 || reqs[w].audio_slot >= audio_cap_) { set_err("encode: bad request"); return false; }
             pj[w] = PackJob{m.raw, m.max_key, m.n_frames, m.n_len, reqs[w].seek};
         }
         if (!ensure_dev_scratch(sizeof(PackJob) * nb)) return false;
@@ -361,6 +366,8 @@ public:
         float* probs = nullptr;           // [S][n_vocab] filtered probabilities of the last round (K6 scratch)
         float* partial = nullptr;
         unsigned int* bar = nullptr;      // device-wide barrier state of the fused projection chains (count, generation)
+        float2* stats = nullptr;          // [40][128] per-tile (mean, M2) of the residual stream (workspace of the fused projections' LayerNorm tail)
+        int* ticket = nullptr;            // "last cluster" ticket of the fused projections
         int* sched = nullptr;             // 2 x (work, exit) counters of the streaming cross-attention kernel: consecutive
         unsigned cross_seq = 0;           // launches alternate, a launch may start its prologue while the previous one drains
         char* pin = nullptr; size_t pin_cap = 0;
@@ -373,6 +380,7 @@ public:
         int last_logit_rows = 0;
         size_t last_logit_base = 0;       // lane-wide index of the first sample whose logits the lane still holds (last chunk only)
         std::chrono::steady_clock::time_point t_submit;
+        double issue_ms = 0, cross_bytes = 0;   // folded into the engine's counters when the round is collected
     };
     int n_lanes() const override { return (int)lanes_.size(); }
 
@@ -394,10 +402,10 @@ public:
     bool decode_submit(int lane, const std::vector<RowDesc>& rows, const std::vector<int>& sample_rows, const std::vector<SampleParams>& sp,
                        float* logits_host, const float* inject, const unsigned char* inject_mask) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "decode: no such lane"; return false; }
+        if (lane < 0 || lane >= (int)lanes_.size()) { set_err("decode: no such lane"); return false; }
         Lane& L = lanes_[lane];
-        if (L.inflight) { err_ = "decode: lane is busy"; return false; }
-        if (sp.size() != sample_rows.size()) { err_ = "decode: params/sample size mismatch"; return false; }
+        if (L.inflight) { set_err("decode: lane is busy"); return false; }
+        if (sp.size() != sample_rows.size()) { set_err("decode: params/sample size mismatch"); return false; }
         L.results.assign(sample_rows.size(), SampleResult{});
         L.pend_S = 0;
         L.inflight = true;
@@ -407,8 +415,11 @@ public:
         CUDA_OK(cudaEventRecord(L.ev[0], L.stream));
         size_t si = 0;
         for (size_t r0 = 0; r0 < rows.size();) {
-            // a chunk holds at most dec_rows_ rows and dec_samples_ sample rows
-            size_t r1 = std::min(rows.size(), r0 + (size_t)dec_rows_);
+            // a chunk holds at most dec_rows_ rows and dec_samples_ sample rows; a step-sized round that is a little too big for the
+            // step kernels (R <= 128) is cut into equal chunks that all take them instead of one pass through the prefill path
+            size_t limit = (size_t)dec_rows_;
+            if (use_skinny_ && sizeof(T) == 2 && rows.size() > 128 && rows.size() <= 512) limit = (rows.size() + (rows.size() + 127) / 128 - 1) / ((rows.size() + 127) / 128);
+            size_t r1 = std::min(rows.size(), r0 + limit);
             size_t sj = si;
             while (sj < sample_rows.size() && (size_t)sample_rows[sj] < r1) {
                 if (sj - si == (size_t)dec_samples_) {
@@ -422,7 +433,7 @@ public:
                 }
                 ++sj;
             }
-            if (r1 == r0) { err_ = "decode: cannot make progress"; L.inflight = false; return false; }
+            if (r1 == r0) { set_err("decode: cannot make progress"); L.inflight = false; return false; }
             const bool last = r1 == rows.size();
             if (!decode_chunk(L, rows.data() + r0, (int)(r1 - r0), sample_rows.data() + si, (int)(sj - si), (int)r0, sp.data() + si, si,
                               logits_host ? logits_host + si * (size_t)hp_.n_vocab : nullptr, inject ? inject + si * (size_t)hp_.n_vocab : nullptr,
@@ -437,18 +448,24 @@ public:
 
     bool decode_collect(int lane, std::vector<SampleResult>& results) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "decode: no such lane"; return false; }
+        if (lane < 0 || lane >= (int)lanes_.size()) { set_err("decode: no such lane"); return false; }
         Lane& L = lanes_[lane];
-        if (!L.inflight) { err_ = "decode: nothing in flight on this lane"; return false; }
+        if (!L.inflight) { set_err("decode: nothing in flight on this lane"); return false; }
         L.inflight = false;
         const auto t0 = std::chrono::steady_clock::now();
         if (!finish_chunk(L)) return false;
-        host_wait_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (L.has_events) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]) == cudaSuccess) stats.ms_decode += ms;
+        const double waited = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        {
+            std::lock_guard<std::mutex> stats_lock(stats_mu_);
+            host_wait_ms_ += waited;
+            host_issue_ms_ += L.issue_ms; L.issue_ms = 0;
+            stats.dec_cross_bytes += L.cross_bytes; L.cross_bytes = 0;
+            if (L.has_events) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]) == cudaSuccess) stats.ms_decode += ms;
+            }
+            collect_marks(L.tm);
         }
-        collect_marks(L.tm);
         results = L.results;
         return true;
     }
@@ -543,13 +560,22 @@ public:
                 mark_begin(Ln.tm, timed || detail_);
                 if (!cross_attention(Ln, drows, R, Ln.qkv, d, ck, cv, Ln.att, cross_slot, cross_head)) return false;
             }
-            if (timed) { mark_end(Ln.tm, true, 2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out projection + residual + MLP LayerNorm
                 SkinnyEpilogue e;
                 e.bias = L.bco; e.x = Ln.x; e.ln_g = L.ln2_g; e.ln_b = L.ln2_b; e.y = Ln.y;
                 if (!proj(Ln.att, d, L.wco, d, e)) return false;
             }
-            {   // FC1 + GELU
+            if (fc1_fused_ && dec_proj_supported(R, 4 * d, d)) {
+                // FC1 + GELU in ONE launch (decode_proj_sm100.cu): nothing after it needs whole rows, so the K split is reduced inside a
+                // 2-CTA cluster and bias + GELU + the bf16 store happen in the same kernel — one dependent step less per layer
+                ProjDesc p;
+                p.R = R; p.N = 4 * d; p.K = d; p.W = reinterpret_cast<const bf16*>(L.w1); p.X = y; p.ldx = d; p.bias = L.b1; p.act = 1;
+                p.out = reinterpret_cast<bf16*>(Ln.h); p.out_ld = 4 * d;
+                mark_begin(Ln.tm, detail_);
+                if (!launch_dec_proj_sm100(p, st)) return gemm_fail();
+                mark_end(Ln.tm, detail_, 10);
+            } else {   // FC1 + GELU
                 SkinnyEpilogue e;
                 e.bias = L.b1; e.act = 1; e.out = Ln.h; e.out_ld = 4 * d;
                 if (!proj(y, d, L.w1, 4 * d, e)) return false;
@@ -560,6 +586,81 @@ public:
                 if (l + 1 < Ld) { e.ln_g = dec_[l + 1].ln1_g; e.ln_b = dec_[l + 1].ln1_b; e.y = Ln.y; }
                 if (!proj(Ln.h, 4 * d, L.w2, d, e)) return false;
             }
+        }
+        return true;
+    }
+
+    // Step batches with the fused cluster projections (decode_proj_sm100.cu): per layer
+    //   self-attention -> [out-proj + residual + LN] -> [cross-query] -> cross-attention -> [cross-out + residual + LN]
+    //   -> [FC1 + GELU] -> [FC2 + residual + next LN] -> [next QKV + KV append]
+    // = 8 launches; no split-K partials in global memory, no epilogue or LayerNorm kernel between two projections.
+    bool decode_layers_proj(Lane& Ln, const RowDesc* drows, int R) {
+        const int d = d_, Ld = hp_.n_text_layer, ntc = hp_.n_text_ctx;
+        cudaStream_t st = Ln.stream;
+        const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
+        const size_t self_slot = (size_t)Ld * 2 * self_kv;
+        const size_t cross_kv = (size_t)kWinRows * d;
+        const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
+        bf16* const y = reinterpret_cast<bf16*>(Ln.y);
+        bf16* const qkv = reinterpret_cast<bf16*>(Ln.qkv);
+        bf16* const att = reinterpret_cast<bf16*>(Ln.att);
+        bf16* const hbuf = reinterpret_cast<bf16*>(Ln.h);
+        auto run = [&](ProjDesc& p) -> bool {
+            p.R = R;
+            mark_begin(Ln.tm, detail_);
+            if (!launch_dec_proj_sm100(p, st)) return gemm_fail();
+            mark_end(Ln.tm, detail_, 10);
+            return true;
+        };
+        // x += X * W^T + b, then y = LayerNorm(x) * g + be
+        auto residual = [&](const bf16* X, int K, const T* W, const float* b, const float* g, const float* be) -> bool {
+            ProjDesc p;
+            p.N = d; p.K = K; p.W = reinterpret_cast<const bf16*>(W); p.X = X; p.ldx = K; p.bias = b; p.x = Ln.x;
+            if (g) { p.y = y; p.ln_g = g; p.ln_b = be; p.stats_out = Ln.stats; p.ticket = Ln.ticket; }
+            return run(p);
+        };
+        auto qkv_proj = [&](int l) -> bool {
+            const Layer<T>& L = dec_[l];
+            bf16* kc = reinterpret_cast<bf16*>(self_pool_ + (size_t)l * 2 * self_kv);
+            ProjDesc p;
+            p.N = 3 * d; p.K = d; p.W = reinterpret_cast<const bf16*>(L.wqkv); p.X = y; p.ldx = d; p.bias = L.bqkv;
+            p.out = qkv; p.out_ld = 3 * d;
+            p.rows = drows; p.kpanel = kc; p.vpanel = kc + self_kv; p.slot_stride = self_slot; p.n_pos_cap = ntc; p.d = d;
+            return run(p);
+        };
+        launch_layernorm<T>(Ln.x, d, dec_[0].ln1_g, dec_[0].ln1_b, Ln.y, d, R, d, st);   // the embedding kernel leaves x only
+        if (!qkv_proj(0)) return false;
+        for (int l = 0; l < Ld; ++l) {
+            const Layer<T>& L = dec_[l];
+            T* kc = self_pool_ + (size_t)l * 2 * self_kv;
+            T* vc = kc + self_kv;
+            mark_begin(Ln.tm, detail_);
+            launch_dec_attention<T>(drows, R, Ln.qkv, 3 * d, kc, vc, Ln.att, d, hp_.n_text_head, /*cross=*/0, self_slot, self_head, 0, st);
+            mark_end(Ln.tm, detail_, 12);
+            if (!residual(att, d, L.wo, L.bo, L.lnc_g, L.lnc_b)) return false;
+            {   // cross-attention query
+                ProjDesc p;
+                p.N = d; p.K = d; p.W = reinterpret_cast<const bf16*>(L.wcq); p.X = y; p.ldx = d; p.bias = L.bcq; p.out = qkv; p.out_ld = d;
+                if (!run(p)) return false;
+            }
+            const T* ck = cross_pool_ + (size_t)l * 2 * cross_kv;
+            const T* cv = ck + cross_kv;
+            const bool timed = profiling && (l % kCrossSample) == 0;
+            mark_begin(Ln.tm, timed || detail_);
+            if (!launch_dec_cross_attention_tc_sm100(drows, R, qkv, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
+                                                     (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), att, d, hp_.n_text_head, cross_slot, hp_.n_audio_ctx,
+                                                     Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st))
+                return gemm_fail();
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (!residual(att, d, L.wco, L.bco, L.ln2_g, L.ln2_b)) return false;
+            {   // FC1 + GELU
+                ProjDesc p;
+                p.N = 4 * d; p.K = d; p.W = reinterpret_cast<const bf16*>(L.w1); p.X = y; p.ldx = d; p.bias = L.b1; p.act = 1; p.out = hbuf; p.out_ld = 4 * d;
+                if (!run(p)) return false;
+            }
+            const bool more = l + 1 < Ld;   // FC2 + residual (+ the next layer's first LayerNorm)
+            if (!residual(hbuf, 4 * d, L.w2, L.b2, more ? dec_[l + 1].ln1_g : nullptr, more ? dec_[l + 1].ln1_b : nullptr)) return false;
+            if (more && !qkv_proj(l + 1)) return false;
         }
         return true;
     }
@@ -646,7 +747,7 @@ public:
                                                      (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
                                                      cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
                 return gemm_fail();
-            if (timed) { mark_end(Ln.tm, true, 2); stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out-projection + residual + MLP LayerNorm, FC1 + GELU, FC2 + residual + next LayerNorm, next layer's QKV
                 Chain c;
                 SkinnyEpilogue& e1 = add(c, att, d, L.wco, d);
@@ -714,7 +815,7 @@ public:
         for (int r = 0; r < R; ++r) {
             const RowDesc& rd = rows[r];
             if (rd.token < 0 || rd.token >= hp_.n_vocab || rd.pos < 0 || rd.pos >= ntc || rd.kv_slot < 0 || rd.kv_slot >= kv_cap_ ||
-                rd.audio_slot < 0 || rd.audio_slot >= audio_cap_) { err_ = "decode: bad row"; return false; }
+                rd.audio_slot < 0 || rd.audio_slot >= audio_cap_) { set_err("decode: bad row"); return false; }
         }
         const size_t rows_bytes = align_up(sizeof(RowDesc) * R, 256), idx_bytes = align_up(sizeof(int) * std::max(S, 1), 256);
         const size_t sp_bytes = align_up(sizeof(SampleParams) * std::max(S, 1), 256), res_bytes = align_up(sizeof(SampleResult) * std::max(S, 1), 256);
@@ -748,7 +849,10 @@ public:
                 distinct = std::adjacent_find(slots.begin(), slots.end()) == slots.end();
             }
             const bool chain = use_chain_ && cross_mode_ == 2 && fuse_cross_q_;
-            if (!(chain ? decode_layers_chain(Ln, drows, R, distinct) : decode_layers_skinny(Ln, drows, R, distinct))) return false;
+            const bool proj = use_proj_ && dec_proj_supported(R, d, d) && dec_proj_supported(R, 3 * d, d) && dec_proj_supported(R, 4 * d, d) &&
+                              dec_proj_supported(R, d, 4 * d);
+            if (proj) { if (!decode_layers_proj(Ln, drows, R)) return false; }
+            else if (!(chain ? decode_layers_chain(Ln, drows, R, distinct) : decode_layers_skinny(Ln, drows, R, distinct))) return false;
         } else {
             for (int l = 0; l < Ld; ++l) {
                 const Layer<T>& L = dec_[l];
@@ -766,7 +870,7 @@ public:
                 mark_begin(Ln.tm, profiling);
                 launch_dec_attention<T>(drows, R, Ln.qkv, d, ck, cv, Ln.att, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, st);
                 mark_end(Ln.tm, profiling, 2);
-                if (profiling) stats.dec_cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T);
+                if (profiling) Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T);
                 { Epilogue e; e.bias = L.bco; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.att, d, L.wco, d, Ln.x, d, R, d, d, e, st)) return gemm_fail(); }
                 launch_layernorm<T>(Ln.x, d, L.ln2_g, L.ln2_b, Ln.y, d, R, d, st);
                 { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(Ln.y, d, L.w1, d, Ln.h, 4 * d, R, 4 * d, d, e, st)) return gemm_fail(); }
@@ -793,7 +897,7 @@ public:
             Ln.pend_off = res_off;
             Ln.pend_pin_off = rows_bytes + idx_bytes + sp_bytes;
         }
-        host_issue_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        Ln.issue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
         Ln.last_logit_rows = S;
         Ln.last_logit_base = res_off;
         return true;
@@ -801,11 +905,11 @@ public:
 
     bool lang_probs(int lane, int sample_index, float* probs_host, int* best) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "lang_probs: no such lane"; return false; }
+        if (lane < 0 || lane >= (int)lanes_.size()) { set_err("lang_probs: no such lane"); return false; }
         Lane& L = lanes_[lane];
         // only the last chunk's logits are still in the lane's buffer: index relative to it
         const long local = (long)sample_index - (long)L.last_logit_base;
-        if (L.inflight || local < 0 || local >= L.last_logit_rows) { err_ = "lang_probs: the logits of that sample row are no longer held by the lane"; return false; }
+        if (L.inflight || local < 0 || local >= L.last_logit_rows) { set_err("lang_probs: the logits of that sample row are no longer held by the lane"); return false; }
         sample_index = (int)local;
         CUDA_OK(cudaStreamSynchronize(L.stream));
         if (!lane_scratch(L, 1024)) return false;
@@ -823,9 +927,9 @@ public:
     bool kv_copy(int lane, const std::vector<KvCopy>& pairs) override {
         CUDA_OK(cudaSetDevice(device_));
         if (pairs.empty()) return true;
-        if (lane < 0 || lane >= (int)lanes_.size()) { err_ = "kv_copy: no such lane"; return false; }
+        if (lane < 0 || lane >= (int)lanes_.size()) { set_err("kv_copy: no such lane"); return false; }
         Lane& L = lanes_[lane];
-        if (L.inflight) { err_ = "kv_copy: lane is busy"; return false; }
+        if (L.inflight) { set_err("kv_copy: lane is busy"); return false; }
         const size_t bytes = sizeof(KvCopy) * pairs.size();
         if (!lane_pin(L, bytes) || !lane_scratch(L, bytes)) return false;
         CUDA_OK(cudaStreamSynchronize(L.stream));
@@ -878,7 +982,7 @@ public:
     // ------------------------------------------------------------------ inspection
     bool export_mel(const DeviceMel& m, float* out) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (!m.raw) { err_ = "no mel"; return false; }
+        if (!m.raw) { set_err("no mel"); return false; }
         const size_t n = (size_t)m.n_len * m.n_mel;
         if (!ensure_dev_scratch(n * sizeof(float))) return false;
         launch_export_mel(m.raw, m.max_key, m.n_frames, m.n_len, m.n_mel, reinterpret_cast<float*>(dev_scratch_), stream_);
@@ -888,7 +992,7 @@ public:
     }
     bool export_encoder_output(int slot, float* out) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (slot < 0 || slot >= audio_cap_) { err_ = "bad slot"; return false; }
+        if (slot < 0 || slot >= audio_cap_) { set_err("bad slot"); return false; }
         const int n = hp_.n_audio_ctx;
         if (!ensure_dev_scratch((size_t)n * d_ * sizeof(float))) return false;
         launch_convert_2d<T, float>(encout_pool_ + (size_t)slot * kWinRows * d_, d_, reinterpret_cast<float*>(dev_scratch_), d_, n, d_, stream_);
@@ -898,7 +1002,7 @@ public:
     }
     bool export_cross_kv(int slot, int layer, float* k, float* v) override {
         CUDA_OK(cudaSetDevice(device_));
-        if (slot < 0 || slot >= audio_cap_ || layer < 0 || layer >= hp_.n_text_layer) { err_ = "bad slot/layer"; return false; }
+        if (slot < 0 || slot >= audio_cap_ || layer < 0 || layer >= hp_.n_text_layer) { set_err("bad slot/layer"); return false; }
         const int n = hp_.n_audio_ctx;
         const size_t ldx = (size_t)2 * hp_.n_text_layer * d_;
         const size_t bytes = (size_t)n * d_ * sizeof(float);
@@ -919,7 +1023,7 @@ public:
 
 private:
     bool gemm_fail() {
-        if (err_.empty()) err_ = std::string("GEMM launch failed: ") + sm100_last_error();
+        set_err(std::string("GEMM launch failed: ") + sm100_last_error(), /*keep_first=*/true);
         return false;
     }
     bool ensure_pin(size_t bytes) {
@@ -1109,7 +1213,7 @@ private:
             if (!upload_ok_) return false;
             weight_bytes_ = a.used;
         } catch (const std::exception& e) {
-            err_ = e.what();
+            set_err(e.what());
             return false;
         }
         // mel tables
@@ -1164,6 +1268,11 @@ private:
         // Off by default: measured on B200 (profiles/r2_chain_*.txt) a device-wide barrier costs 1.9 us — the same as a PDL launch
         // boundary — and the chain needs two per projection, so the fused grid is ~5 % SLOWER than twelve small launches.
         use_chain_ = env_int("NOBS_WHISPER_CHAIN", 0) != 0 && !f32 && chain_fits(n_lanes, chain_stages_);
+        // Opt-in: one cluster launch per projection (decode_proj_sm100.cu), 8 launches per layer.  Measured slower in the 2-3 lane step than
+        // the split-K GEMM + epilogue pairs (profiles/README.md, round 2): each fused kernel has the serial phases of two, and an
+        // 8-CTA cluster is placed later than single CTAs while another lane's attention CTAs hold every SM.
+        use_proj_ = env_int("NOBS_WHISPER_PROJ", 0) != 0 && !f32 && cross_mode_ == 2;
+        fc1_fused_ = env_int("NOBS_WHISPER_FC1_FUSED", 1) != 0 && !f32;
         // The encoder and every decode lane own their activations: a lane may decode while the encoder
         // works on other windows and while other lanes decode.
         auto plan_enc = [&](Arena& a) {
@@ -1186,6 +1295,8 @@ private:
             L.partial = (float*)a.take((size_t)16 << 20);  // skinny-GEMM split-K partials: <= 4 splits x 128 rows x 5120 cols (FC1) fp32
             L.sched = (int*)a.take(256);
             L.bar = (unsigned int*)a.take(256);
+            L.stats = (float2*)a.take(40 * 128 * sizeof(float2));
+            L.ticket = (int*)a.take(256);
             L.ys = (T*)a.take(S * d * sizeof(T));
             L.logits = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
             L.probs = (float*)a.take(S * (size_t)hp_.n_vocab * sizeof(float));
@@ -1258,12 +1369,19 @@ private:
     bool use_skinny_ = true;
     int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
     int cross_ctas_ = 0;              // > 0: cap that kernel's grid
+    bool fc1_fused_ = true;           // step batches: FC1 + GELU as one cluster launch instead of split-K GEMM + epilogue kernel
+    bool use_proj_ = false;           // step batches: fused cluster projections (split-K reduced in DSMEM, LayerNorm split around the kernel boundary)
     bool use_chain_ = true;           // step batches: projection chains between the attention kernels as single persistent launches
     int chain_stages_ = 3;
     bool fuse_qkv_ = true;            // single-token steps: the self-attention kernel finishes the QKV projection's split-K sums
     bool skinny_logits_ = true;       // step batches: logits through the swap-AB weight-streaming GEMM
     bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
+    std::mutex enc_mu_, stats_mu_, err_mu_;
+    void set_err(const std::string& e, bool keep_first = false) {
+        std::lock_guard<std::mutex> lock(err_mu_);
+        if (!keep_first || err_.empty()) err_ = e;
+    }
     double host_issue_ms_ = 0, host_wait_ms_ = 0;  // decode_chunk: time spent issuing launches vs waiting for the GPU
     double detail_ms_[8] = {};
     long detail_n_[8] = {};

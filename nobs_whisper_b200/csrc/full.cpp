@@ -5,9 +5,12 @@
 // path: language auto-detect, prompt assembly,
 // temperature fallback, timestamp-driven seek, segment splitting.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 #include "state.h"
 
@@ -42,6 +45,19 @@ struct Candidate {
 
 enum class Phase { LangDetect, Window, Prefill, Step, Finished };
 
+// The first fallback pass of a window, decoded speculatively NEXT TO pass 0 (see Driver::shadow_* below).
+struct Shadow {
+    bool on = false;      // exists for the current window
+    bool done = false;    // finished (completed / failed / token budget): waiting for pass 0's verdict
+    Dec dec;
+    std::vector<whisper_token> prompt;
+    int step = 0;
+    int sample = -1;      // index of its sample in the lane's round in flight (-1: none)
+    bool prefill = false; // that sample is the pass's first (sampled from the prompt)
+    float no_speech_prob = 0.0f;
+    std::mt19937 rng0;    // decoder 0's generator as it was before the shadow drew from it
+};
+
 struct Job {
     whisper_state* st = nullptr;
     whisper_full_params p{};
@@ -59,6 +75,8 @@ struct Job {
     // bookkeeping of the round in flight
     int first_sample = -1, n_samples = 0;
     std::vector<int> live;  // decoder index of each sample of this round
+    bool speculate = false; // this audio may run a shadow pass (greedy, best_of 1, pass 0 is argmax, a fallback temperature exists)
+    Shadow sh;
 };
 
 whisper_token_data make_token(const SampleResult& r, int id, float p, float plog, int default_tid, int token_beg) {
@@ -107,6 +125,8 @@ class Driver {
         std::vector<SampleParams> sp;
         std::vector<SampleResult> res;
         std::vector<KvCopy> kv_pairs_a, kv_pairs_b;
+        std::vector<EncodeRequest> enc;        // windows of this lane's audios that are due for the encoder
+        std::string error;                     // error text raised on this lane's thread (handed to the caller's thread at the end)
         std::vector<float> inject;             // scripted-logits test hook: replacement logits per sample of the round
         std::vector<unsigned char> inject_mask;
         bool inflight = false;
@@ -161,43 +181,38 @@ public:
             lanes_.assign(n_lanes_, LaneState());
             for (int i = 0; i < n; ++i) lanes_[jobs_[i].lane].jobs.push_back(i);
         }
-        // ---- rounds: every lane alternates "collect results, advance its audios, queue the next round";
-        // while the host works on one lane the others keep the GPU busy.
-        while (true) {
-            bool active = false;
+        // ---- rounds: every lane alternates "collect results, advance its audios, queue the next round".  With several lanes each
+        // lane is driven by its own host thread: a round is ~400 launches (~2 ms of host time), and a single thread that is busy
+        // issuing one lane's round leaves every other lane that finishes meanwhile idle until it gets back to it.  The lanes share
+        // nothing but the encoder (Engine::encode is serialised inside the engine) and read-only weights; audios never change lane.
+        // The scripted-logits test hook calls back into the test in a fixed order: it keeps the single-threaded loop.
+        static const bool threads_ok = [] { const char* v = getenv("NOBS_WHISPER_HOST_THREADS"); return !(v && *v == '0'); }();
+        if (n_lanes_ > 1 && threads_ok && !ctx_->logits_hook) {
+            std::atomic<int> failed{0};
+            std::vector<std::thread> workers;
             for (int ln = 0; ln < n_lanes_; ++ln) {
-                LaneState& L = lanes_[ln];
-                if (L.inflight) {
-                    L.inflight = false;
-                    if (!eng_.decode_collect(ln, L.res)) return fail_all(rc, n, -8);
-                    for (int i : L.jobs) consume(jobs_[i]);
-                    if (!L.kv_pairs_a.empty()) {
-                        if (!eng_.kv_copy(ln, L.kv_pairs_a)) return fail_all(rc, n, -8);
-                        if (!L.kv_pairs_b.empty() && !eng_.kv_copy(ln, L.kv_pairs_b)) return fail_all(rc, n, -8);
+                workers.emplace_back([this, ln, &failed] {
+                    while (!failed.load(std::memory_order_relaxed)) {
+                        bool active = false;
+                        const int code = lane_step(ln, active);
+                        if (code != 0) { int expected = 0; failed.compare_exchange_strong(expected, code); break; }
+                        if (!active) break;
                     }
-                }
-                while (true) {
-                    if (!encode_round(L)) return fail_all(rc, n, -6);
-                    L.rows.clear(); L.samp.clear(); L.sp.clear();
-                    L.kv_pairs_a.clear(); L.kv_pairs_b.clear();
-                    L.inject_mask.clear();
-                    bool any = false;
-                    for (int i : L.jobs) any |= emit_rows(jobs_[i]);
-                    if (any) {
-                        const bool scripted = !L.inject_mask.empty();
-                        if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr, scripted ? L.inject.data() : nullptr, scripted ? L.inject_mask.data() : nullptr))
-                            return fail_all(rc, n, -8);
-                        L.inflight = true;
-                        active = true;
-                        break;
-                    }
-                    bool pending = false;
-                    for (int i : L.jobs) pending |= (jobs_[i].phase == Phase::Window);
-                    if (!pending) break;  // otherwise: windows that still have to be encoded
-                }
+                });
             }
-            if (!active) break;
+            for (auto& w : workers) w.join();
+            if (failed.load()) return fail_all(rc, n, failed.load());
+        } else {
+            while (true) {
+                bool active = false;
+                for (int ln = 0; ln < n_lanes_; ++ln) {
+                    const int code = lane_step(ln, active);
+                    if (code != 0) return fail_all(rc, n, code);
+                }
+                if (!active) break;
+            }
         }
+        for (const LaneState& L : lanes_) if (!L.error.empty()) set_last_error(L.error);
         const long launches = kernel_launch_count() - launches0;
         for (int i = 0; i < n; ++i) {
             rc[i] = jobs_[i].rc;
@@ -218,6 +233,40 @@ public:
     }
 
 private:
+    // One turn of a lane: take the results of its round in flight (if any), advance its audios, encode the windows that
+    // became due, and queue the next round.  Returns 0, or the whisper_full error code; sets `active` if a round was queued.
+    int lane_step(int ln, bool& active) {
+        LaneState& L = lanes_[ln];
+        if (L.inflight) {
+            L.inflight = false;
+            if (!eng_.decode_collect(ln, L.res)) return -8;
+            for (int i : L.jobs) consume(jobs_[i]);
+            if (!L.kv_pairs_a.empty()) {
+                if (!eng_.kv_copy(ln, L.kv_pairs_a)) return -8;
+                if (!L.kv_pairs_b.empty() && !eng_.kv_copy(ln, L.kv_pairs_b)) return -8;
+            }
+        }
+        while (true) {
+            if (!encode_round(L)) return -6;
+            L.rows.clear(); L.samp.clear(); L.sp.clear();
+            L.kv_pairs_a.clear(); L.kv_pairs_b.clear();
+            L.inject_mask.clear();
+            bool any = false;
+            for (int i : L.jobs) any |= emit_rows(jobs_[i]);
+            if (any) {
+                const bool scripted = !L.inject_mask.empty();
+                if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr, scripted ? L.inject.data() : nullptr, scripted ? L.inject_mask.data() : nullptr))
+                    return -8;
+                L.inflight = true;
+                active = true;
+                return 0;
+            }
+            bool pending = false;
+            for (int i : L.jobs) pending |= (jobs_[i].phase == Phase::Window);
+            if (!pending) return 0;  // otherwise: windows that still have to be encoded
+        }
+    }
+
     int fail_all(int* rc, int n, int code) {
         const std::string first_error = eng_.last_error();
         // other lanes may still have a round in flight: wait for them (results are dropped) so that no kernel writes the
@@ -232,7 +281,7 @@ private:
         for (int i = 0; i < n; ++i) rc[i] = (jobs_.size() > (size_t)i && jobs_[i].rc != 0) ? jobs_[i].rc : code;
         return code;
     }
-    int kv_needed(const Job& j) const { return j.p.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? 2 * j.n_decoders : j.n_decoders; }
+    int kv_needed(const Job& j) const { return j.p.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? 2 * j.n_decoders : j.n_decoders + (j.speculate ? 1 : 0); }
 
     // Everything whisper_full does before its main loop.  Returns the number of KV slots needed.
     int setup_job(Job& j) {
@@ -255,6 +304,15 @@ private:
         j.n_decoders = p.strategy == WHISPER_SAMPLING_GREEDY ? p.greedy.best_of : std::max(p.greedy.best_of, p.beam_search.beam_size);
         j.n_decoders = std::max(1, j.n_decoders);
         if (j.n_decoders > WHISPER_MAX_DECODERS) { j.rc = -4; j.phase = Phase::Finished; return 0; }
+        // Speculative first fallback (shadow pass): with the reference's parameters (greedy, best_of 1, temperature ladder 0, 0.2, ...)
+        // pass 0 is an argmax decode that never touches the decoder's generator, so pass 1 — should it be needed — starts from a
+        // generator state that is known up front.  It is decoded in the same rounds as pass 0 from its own KV slot: if pass 0 is
+        // accepted the shadow is dropped and the generator restored, otherwise pass 1 is already (partly) done.  Token for token
+        // the result is the sequential one; a round carries up to two rows per audio that share one cross-KV panel stream.
+        const char* spec_env = getenv("NOBS_WHISPER_SPECULATE");   // read per call: tests and A/B runs toggle it between calls
+        const bool spec_ok = !(spec_env && *spec_env == '0');
+        j.speculate = spec_ok && !ctx_->logits_hook && p.strategy == WHISPER_SAMPLING_GREEDY && p.greedy.best_of <= 1 && j.temps.size() >= 2 &&
+                      j.temps[0] < 1e-6f && j.temps[1] > 1e-6f && j.n_decoders + 1 <= WHISPER_MAX_DECODERS;
         if (p.strategy == WHISPER_SAMPLING_BEAM_SEARCH && p.beam_search.beam_size > kMaxTopK) { j.rc = -4; j.phase = Phase::Finished; return 0; }
         if (p.audio_ctx > hp_.n_audio_ctx) { j.rc = -5; j.phase = Phase::Finished; return 0; }
         {
@@ -302,7 +360,13 @@ private:
         j.prompt_init = {vocab_.token_sot};
         if (vocab_.is_multilingual()) {
             const int lid = lang_id(j.lang.c_str());
-            if (lid < 0) { j.rc = -3; j.phase = Phase::Finished; set_last_error("unknown language '" + j.lang + "'"); return false; }
+            if (lid < 0) {
+                j.rc = -3; j.phase = Phase::Finished;
+                const std::string msg = "unknown language '" + j.lang + "'";
+                if (j.lane >= 0 && j.lane < (int)lanes_.size()) lanes_[j.lane].error = msg;   // may run on a lane's thread: the error text is thread-local
+                set_last_error(msg);
+                return false;
+            }
             j.st->lang_id = lid;
             j.prompt_init.push_back(vocab_.token_lang(lid));
             j.prompt_init.push_back(j.p.translate ? vocab_.token_translate : vocab_.token_transcribe);
@@ -313,6 +377,7 @@ private:
 
     // Encode every window that is due (language-detect windows included), as one batch.
     bool encode_round(LaneState& L) {
+        std::vector<EncodeRequest>& enc_ = L.enc;
         enc_.clear();
         for (int ji : L.jobs) {
             Job& j = jobs_[ji];
@@ -428,6 +493,8 @@ private:
             st->stats.n_decode_rows += (int64_t)j.prompt.size();
             st->stats.n_sample_rows += j.n_cur;
             st->stats.n_decode_rounds++;
+            j.sh.sample = -1;
+            if (j.it == 0) { j.sh = Shadow(); if (j.speculate) shadow_prefill(j); }
             return true;
         }
         if (j.phase == Phase::Step) {
@@ -448,9 +515,85 @@ private:
             st->stats.n_decode_rows += j.n_samples;
             st->stats.n_sample_rows += j.n_samples;
             st->stats.n_decode_rounds++;
+            j.sh.sample = -1;
+            if (j.it == 0 && j.sh.on && !j.sh.done && j.n_samples > 0) shadow_step(j);
             return j.n_samples > 0;
         }
         return false;
+    }
+
+    // ---- shadow pass (see setup_job): rows of temperature pass 1 queued next to pass 0's
+    void shadow_prefill(Job& j) {
+        LaneState& L = lanes_[j.lane];
+        whisper_state* st = j.st;
+        Shadow& sh = j.sh;
+        const float t1 = j.temps[1];
+        sh.on = true;
+        sh.rng0 = st->rng[0];
+        sh.dec.seq = Sequence();
+        sh.dec.seek_delta = 100 * kChunk;
+        sh.dec.failed = sh.dec.completed = sh.dec.has_ts = false;
+        sh.prompt.clear();
+        if (!st->prompt_past.empty() && t1 < 0.5f && j.p.n_max_text_ctx > 0) {
+            const int n_take = std::min(std::min(j.p.n_max_text_ctx, hp_.n_text_ctx / 2), (int)st->prompt_past.size());
+            sh.prompt.push_back(vocab_.token_prev);
+            sh.prompt.insert(sh.prompt.end(), st->prompt_past.end() - n_take, st->prompt_past.end());
+        }
+        sh.prompt.insert(sh.prompt.end(), j.prompt_init.begin(), j.prompt_init.end());
+        const int slot = st->kv_slots[j.n_decoders];
+        for (size_t i = 0; i < sh.prompt.size(); ++i) L.rows.push_back(RowDesc{sh.prompt[i], (int)i, slot, st->audio_slot});
+        L.samp.push_back((int)L.rows.size() - 1);
+        SampleParams sp;
+        fill_sample_params(j, sh.dec, t1, /*prefill=*/true, 0, sp);
+        L.sp.push_back(sp);
+        sh.sample = (int)L.samp.size() - 1;
+        sh.prefill = true;
+        sh.step = 0;
+        st->stats.n_decode_rows += (int64_t)sh.prompt.size();
+        st->stats.n_sample_rows += 1;
+    }
+    void shadow_step(Job& j) {
+        LaneState& L = lanes_[j.lane];
+        whisper_state* st = j.st;
+        Shadow& sh = j.sh;
+        L.rows.push_back(RowDesc{sh.dec.seq.tokens.back().id, (int)sh.prompt.size() + sh.step, st->kv_slots[j.n_decoders], st->audio_slot});
+        L.samp.push_back((int)L.rows.size() - 1);
+        SampleParams sp;
+        fill_sample_params(j, sh.dec, j.temps[1], false, 0, sp);
+        L.sp.push_back(sp);
+        sh.sample = (int)L.samp.size() - 1;
+        sh.prefill = false;
+        st->stats.n_decode_rows += 1;
+        st->stats.n_sample_rows += 1;
+    }
+    // apply the shadow's sample of the round just collected (before pass 0 is advanced: its verdict may adopt the shadow)
+    void shadow_consume(Job& j) {
+        Shadow& sh = j.sh;
+        if (!sh.on || sh.sample < 0) return;
+        sh.dec.res = lanes_[j.lane].res[sh.sample];
+        sh.sample = -1;
+        if (sh.prefill) { sh.no_speech_prob = sh.dec.res.no_speech_prob; sh.step = 0; } else sh.step += 1;
+        Dec& d = sh.dec;
+        d.seq.tokens.push_back(make_token(d.res, d.res.id, d.res.p, d.res.plog, 0, vocab_.token_beg));
+        d.seq.sum_logprobs_all += d.res.plog;
+        settle(j, d, sh.step);
+        if (d.completed || d.failed || sh.step == j.n_max - 1) sh.done = true;
+    }
+    // pass 0 was rejected: the shadow becomes the current pass (temperature index 1)
+    void shadow_adopt(Job& j) {
+        whisper_state* st = j.st;
+        Shadow& sh = j.sh;
+        std::swap(st->kv_slots[0], st->kv_slots[j.n_decoders]);
+        j.it = 1;
+        j.n_cur = 1;
+        j.dec[0] = sh.dec;
+        j.prompt = sh.prompt;
+        j.step = sh.step;
+        st->no_speech_prob = sh.no_speech_prob;
+        const bool done = sh.done;
+        sh = Shadow();
+        if (done) finish_temperature(j);
+        else j.phase = Phase::Step;
     }
 
     // Take this job's results of the round and advance its state machine.
@@ -470,6 +613,7 @@ private:
             return;
         }
         for (int s = 0; s < j.n_samples; ++s) j.dec[j.live[s]].res = res_[j.first_sample + s];
+        shadow_consume(j);
         if (j.phase == Phase::Prefill) {
             st->no_speech_prob = res_[j.first_sample].no_speech_prob;
             for (int k = 1; k < j.n_cur; ++k) kv_pairs_a_.push_back(KvCopy{st->kv_slots[0], st->kv_slots[k], (int)j.prompt.size()});
@@ -478,6 +622,30 @@ private:
             j.step += 1;
         }
         advance(j);
+    }
+
+    // The reference's per-decoder rules after token i has been appended: timestamp bookkeeping, completion, failure.
+    void settle(const Job& j, Dec& d, int i) {
+        int& result_len = d.seq.result_len;
+        const whisper_token_data& tok = d.seq.tokens.back();
+        if (tok.id > vocab_.token_beg) {
+            const int seek_delta_new = 2 * (tok.id - vocab_.token_beg);
+            if (d.has_ts && d.seek_delta > seek_delta_new && result_len < i) { d.failed = true; return; }  // went back in time
+            d.seek_delta = seek_delta_new;
+            result_len = i + 1;
+            d.has_ts = true;
+        }
+        if (tok.id == vocab_.token_eot || (j.p.max_tokens > 0 && i >= j.p.max_tokens) ||
+            (d.has_ts && j.seek + d.seek_delta + kDeltaMin >= j.seek_end)) {
+            if (result_len == 0 && !j.p.no_timestamps) {
+                if (j.seek + d.seek_delta + kDeltaMin >= j.seek_end) result_len = i + 1;
+                else { d.failed = true; return; }
+            }
+            if (j.p.single_segment || j.p.no_timestamps) { result_len = i + 1; d.seek_delta = 100 * kChunk; }
+            d.completed = true;
+            return;
+        }
+        if (i == j.n_max - 1 && (result_len == 0 || d.seek_delta < 100 * kChunk / 2)) { d.failed = true; return; }  // repetition guard
     }
 
     // One iteration of the reference's token loop, from "sample" to "all decoders finished?".
@@ -535,26 +703,7 @@ private:
         for (int k = 0; k < j.n_cur; ++k) {
             Dec& d = j.dec[k];
             if (d.completed || d.failed) continue;
-            int& result_len = d.seq.result_len;
-            const whisper_token_data& tok = d.seq.tokens.back();
-            if (tok.id > vocab_.token_beg) {
-                const int seek_delta_new = 2 * (tok.id - vocab_.token_beg);
-                if (d.has_ts && d.seek_delta > seek_delta_new && result_len < i) { d.failed = true; continue; }  // went back in time
-                d.seek_delta = seek_delta_new;
-                result_len = i + 1;
-                d.has_ts = true;
-            }
-            if (tok.id == vocab_.token_eot || (j.p.max_tokens > 0 && i >= j.p.max_tokens) ||
-                (d.has_ts && j.seek + d.seek_delta + kDeltaMin >= j.seek_end)) {
-                if (result_len == 0 && !j.p.no_timestamps) {
-                    if (j.seek + d.seek_delta + kDeltaMin >= j.seek_end) result_len = i + 1;
-                    else { d.failed = true; continue; }
-                }
-                if (j.p.single_segment || j.p.no_timestamps) { result_len = i + 1; d.seek_delta = 100 * kChunk; }
-                d.completed = true;
-                continue;
-            }
-            if (i == j.n_max - 1 && (result_len == 0 || d.seek_delta < 100 * kChunk / 2)) { d.failed = true; continue; }  // repetition guard
+            settle(j, d, i);
         }
         bool all_done = true;
         for (int k = 0; k < j.n_cur; ++k) if (!(j.dec[k].completed || j.dec[k].failed)) all_done = false;
@@ -583,9 +732,14 @@ private:
         }
         if (!success) {
             st->stats.n_fallbacks++;
+            if (j.it == 0 && j.sh.on) { shadow_adopt(j); return; }
             j.it += 1;
             j.phase = Phase::Prefill;
             return;
+        }
+        if (j.sh.on) {   // pass 0 accepted: as if the shadow had never drawn from the generator
+            st->rng[0] = j.sh.rng0;
+            j.sh = Shadow();
         }
         emit_segments(j);
         j.phase = Phase::Window;
@@ -642,7 +796,6 @@ private:
     const Vocab& vocab_;
     const HParams& hp_;
     std::vector<Job> jobs_;
-    std::vector<EncodeRequest> enc_;
     std::vector<LaneState> lanes_;
     int n_lanes_ = 1;
 };

@@ -59,6 +59,36 @@ struct ChainDesc {
 };
 // W[i]: [N_i][K_i] weights, X[i]: [R][ldx[i]] activations of step i.  stages: shared-memory ring depth (2 or 3).
 bool launch_dec_chain_sm100(ChainDesc& cd, const bf16* const* W, const bf16* const* X, const int* ldx, int stages, cudaStream_t s);
+// Fused decoder-step projection (decode_proj_sm100.cu): v = X * W^T + bias for R <= 128 token rows in ONE launch — split-K over a
+// thread-block cluster with the partial sums reduced through distributed shared memory; bias / GELU / residual / bf16 store /
+// KV-cache append in the same kernel; and, for a projection that updates the residual stream, y = LayerNorm(x) for the next
+// projection written by whichever cluster finishes last.  N must be a multiple of 128 (at most 40 tiles), K of 64.
+struct ProjDesc {
+    int R = 0, N = 0, K = 0;
+    const bf16* W = nullptr;            // [N][K]
+    const bf16* X = nullptr;            // bf16 activations [R][ldx]
+    int ldx = 0;
+    const float* bias = nullptr;        // [N]
+    int act = 0;                        // 1: GELU
+    float* x = nullptr;                 // residual stream [R][N]: x += v (v becomes the updated x)
+    bf16* out = nullptr;                // [R][out_ld] = v
+    int out_ld = 0;
+    const RowDesc* rows = nullptr;      // if set (QKV): columns [d, 2d) / [2d, 3d) are also appended to the K / V cache panels
+    bf16* kpanel = nullptr;
+    bf16* vpanel = nullptr;
+    size_t slot_stride = 0;
+    int n_pos_cap = 0, d = 0;
+    // LayerNorm of the updated residual stream (needs x): y [R][N] = LN(x) * ln_g + ln_b
+    bf16* y = nullptr;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+    float2* stats_out = nullptr;        // workspace [N / 128][128]: (mean, M2) per 128-feature tile and row
+    int* ticket = nullptr;              // one zero-initialised int owned by the calling stream (re-armed by the kernel)
+};
+bool dec_proj_supported(int R, int N, int K);
+int dec_proj_splits(int N, int K);
+bool launch_dec_proj_sm100(const ProjDesc& a, cudaStream_t s);
+void trace_set_proj(unsigned long long* buf, unsigned int cap);
 int chain_stages_for_lanes(int n_lanes);
 // true when n_lanes concurrent chain grids can always become co-resident (no mutual wait for SM slots)
 bool chain_fits(int n_lanes, int stages);

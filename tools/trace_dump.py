@@ -1,5 +1,6 @@
 """Dump a NOBS_WHISPER_TRACE file as a flat timeline (block 0 of every instrumented decode kernel).
-Kernel ids: 1 skinny GEMM, 2 split-K epilogue, 3 self-attention, 4 cross-attention, 5 tiled GEMM, 7 K6, 8 fused projection chain;
+Kernel ids: 1 skinny GEMM, 2 split-K epilogue, 3 self-attention, 4 cross-attention, 5 tiled GEMM, 7 K6, 8 fused projection chain,
+9 cluster projection (150 / 151 / 152: block 0 parked its tile / the cluster did / block 0 wrote its share);
 100 + id: the moment the kernel's PDL wait returned; chain marks: 110 + s = all partial sums of step s are in (first barrier passed),
 120 + s = step s reduced (second barrier passed).
 usage: trace_dump.py file [t_lo_us t_hi_us]"""
@@ -11,7 +12,7 @@ kid, tag, t0, t1 = a[:, 0].astype(int), a[:, 1], a[:, 2].astype(np.int64), a[:, 
 ok = t0 > 0
 kid, tag, t0, t1 = kid[ok], tag[ok], t0[ok], t1[ok]
 base = t0.min()
-names = {1: "skinny_gemm", 2: "reduce", 3: "self_attn", 4: "cross_attn", 5: "gemm", 7: "k6", 8: "chain"}
+names = {1: "skinny_gemm", 2: "reduce", 3: "self_attn", 4: "cross_attn", 5: "gemm", 7: "k6", 8: "chain", 9: "proj"}
 lo, hi = (float(sys.argv[2]) * 1e3, float(sys.argv[3]) * 1e3) if len(sys.argv) > 3 else (0, 400e3)
 order = np.argsort(t0)
 lanes = {}
@@ -33,6 +34,9 @@ for i in order:
         print(f"{t/1e3:10.2f}  chain        step {k-130} block 0 GEMM done tag {int(tag[i]) & 0xffffffff:08x}")
     elif 140 <= k < 150:
         print(f"{t/1e3:10.2f}  chain        step {k-140} block 0 rows done tag {int(tag[i]) & 0xffffffff:08x}")
+    elif 150 <= k < 153:
+        what = {150: "tile parked", 151: "cluster parked", 152: "reduced + written"}[k]
+        print(f"{t/1e3:10.2f}  proj         {what:24s} tag {int(tag[i]) & 0xffffffff:08x}")
 for k in sorted(set(kid)):
     if k in names:
         m = (kid == k) & (t1 > 0)
