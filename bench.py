@@ -381,6 +381,8 @@ def main():
         roofline = {
             "bound": "hbm", "kernel": "dec_cross_attention_tc_kernel (decoder cross-attention: TMA ring -> tcgen05 over the head-major cross-KV panels)",
             "achieved": cross_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": cross_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
+            # algorithmic bytes count every cross-KV panel ONCE per launch: rows of the same audio (a pass and its speculative successor)
+            # stream the same panels, the second read is served by L2
             # DRAM bytes per launch: ncu --set full of this kernel (profiles/r1_ncu_full_dec_cross_attention_tc.csv, 8 rows per
             # launch) read 63.0-63.7 MB + wrote 1.8-3.7 MB against 61.4 MB algorithmic (the 12th TMA box of a panel covers 36 pad
             # rows; the writes are the attention output and the query tiles); scaled by that ratio to this run's launch size
@@ -424,12 +426,15 @@ def main():
                 "workload": f"whisper {args.model} ({arch.n_mels} mel bins, {arch.n_audio_layer}+{arch.n_text_layer} layers) {args.precision}, "
                             + (f"{n_win} x 30-s windows per GPU (1 h of synthetic 16 kHz audio each; weak scaling)" if args.scaling == "weak" else
                                f"{total_windows} x 30-s windows in total split over {world} GPU(s) ({n_win} on rank 0; strong scaling of the one-hour workload)")
-                            + ", greedy best_of=1 with the reference's temperature fallback",
+                            + ", greedy best_of=1 with the reference's temperature fallback; every clip ends in a sub-second remainder window "
+                              "(whisper.cpp 1.7.6 delta_min = 100 ms), so a step encodes and decodes ~2 windows per clip — twice the work of the round-1 "
+                              "figure, which stopped at 1 s (see DESIGN.md section 6)",
                 "windows_per_gpu": n_win, "windows_total": total_windows, "weights": "random-init N(0,0.02) ggml f16 file, seed 0", "l2": "inputs and weights exceed L2 (3.1 GB weights, 30 GB cross-KV)",
                 "decoder_rows_per_step": agg_dev["rows"] / steps, "sampled_tokens_per_step": agg_dev["samples"] / steps,
                 "decoder_rounds_per_step": agg_dev["rounds"] / steps, "fallbacks_per_step": agg_dev["fallbacks"] / steps,
                 "stage_ms_per_step": {"mel": agg_dev["ms_mel"] / steps, "encode": agg_dev["ms_enc"] / steps,
                                       "decode_lane_sum": agg_dev["ms_dec"] / steps, "decode_lanes": eng.n_lanes()},
+                "speculative_first_fallback": os.environ.get("NOBS_WHISPER_SPECULATE", "1") != "0",
                 "x_realtime": value, "timing": "CUDA events on the library stream around the K steps, max over ranks",
                 "host_wall_ms_per_step": 1000.0 * agg_dev["wall_s"] / steps,
             },

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <unordered_map>
 
 #include "gemm_sm100.cuh"
 
@@ -109,6 +110,7 @@ public:
             if (L.stream) cudaStreamSynchronize(L.stream);
             for (auto& e : L.tm.pool) cudaEventDestroy(e);
             for (auto& e : L.ev) if (e) cudaEventDestroy(e);
+            for (auto& g : L.graphs) cudaGraphExecDestroy(g.second.exec);
             if (L.pin) cudaFreeHost(L.pin);
             if (L.scratch) cudaFree(L.scratch);
             if (L.stream) cudaStreamDestroy(L.stream);
@@ -381,6 +383,12 @@ public:
         size_t last_logit_base = 0;       // lane-wide index of the first sample whose logits the lane still holds (last chunk only)
         std::chrono::steady_clock::time_point t_submit;
         double issue_ms = 0, cross_bytes = 0;   // folded into the engine's counters when the round is collected
+        struct GraphEntry { cudaGraphExec_t exec; long n_kernels; };
+        std::unordered_map<uint64_t, GraphEntry> graphs;   // captured step rounds by shape (decode_chunk)
+        std::unordered_map<uint64_t, int> graph_seen;
+        unsigned graph_epoch = 0;
+        int cross_slots = 0;                    // distinct audio slots among the rows of the chunk being queued: rows of one audio (a pass and its
+                                                // speculative successor, beams) stream the same cross-KV panels, which leave HBM once
     };
     int n_lanes() const override { return (int)lanes_.size(); }
 
@@ -560,7 +568,7 @@ public:
                 mark_begin(Ln.tm, timed || detail_);
                 if (!cross_attention(Ln, drows, R, Ln.qkv, d, ck, cv, Ln.att, cross_slot, cross_head)) return false;
             }
-            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out projection + residual + MLP LayerNorm
                 SkinnyEpilogue e;
                 e.bias = L.bco; e.x = Ln.x; e.ln_g = L.ln2_g; e.ln_b = L.ln2_b; e.y = Ln.y;
@@ -651,7 +659,7 @@ public:
                                                      (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), att, d, hp_.n_text_head, cross_slot, hp_.n_audio_ctx,
                                                      Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st))
                 return gemm_fail();
-            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             if (!residual(att, d, L.wco, L.bco, L.ln2_g, L.ln2_b)) return false;
             {   // FC1 + GELU
                 ProjDesc p;
@@ -747,7 +755,7 @@ public:
                                                      (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
                                                      cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
                 return gemm_fail();
-            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
+            if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out-projection + residual + MLP LayerNorm, FC1 + GELU, FC2 + residual + next LayerNorm, next layer's QKV
                 Chain c;
                 SkinnyEpilogue& e1 = add(c, att, d, L.wco, d);
@@ -826,13 +834,28 @@ public:
         int* hidx = reinterpret_cast<int*>(hp + rows_bytes);
         for (int i = 0; i < S; ++i) hidx[i] = samp[i] - row_base;
         if (S) memcpy(hp + rows_bytes + idx_bytes, sp, sizeof(SampleParams) * S);
-        CUDA_OK(cudaMemcpyAsync(Ln.scratch, hp, rows_bytes + idx_bytes + sp_bytes, cudaMemcpyHostToDevice, st));
         const RowDesc* drows = reinterpret_cast<const RowDesc*>(Ln.scratch);
         const int* didx = reinterpret_cast<const int*>(Ln.scratch + rows_bytes);
         const SampleParams* dsp = reinterpret_cast<const SampleParams*>(Ln.scratch + rows_bytes + idx_bytes);
         SampleResult* dres = reinterpret_cast<SampleResult*>(Ln.scratch + rows_bytes + idx_bytes + sp_bytes);
 
+        bool distinct = true;   // single-token steps: one row per KV slot (selects the kernels of the QKV / self-attention step)
+        {
+            std::vector<int> slots(R);
+            for (int r = 0; r < R; ++r) slots[r] = rows[r].audio_slot;
+            std::sort(slots.begin(), slots.end());
+            Ln.cross_slots = (int)(std::unique(slots.begin(), slots.end()) - slots.begin());
+            for (int r = 0; r < R; ++r) slots[r] = rows[r].kv_slot;
+            std::sort(slots.begin(), slots.end());
+            distinct = std::adjacent_find(slots.begin(), slots.end()) == slots.end();
+        }
         const auto host_t0 = std::chrono::steady_clock::now();
+        // ---- everything queued on the lane's stream for this chunk.  For small step batches (the single-utterance path: 1-8 rows)
+        // the sequence depends on (R, S) and on buffer addresses only — tokens, positions, slots, sampling parameters travel through
+        // the pinned staging — so it is captured once as a CUDA graph (programmatic-dependent-launch edges included) and replayed:
+        // a round of a 4-layer decoder is ~60 launches, ~0.3 ms of host time that the GPU finishes faster than the host can issue.
+        auto issue = [&]() -> bool {
+        CUDA_OK(cudaMemcpyAsync(Ln.scratch, hp, rows_bytes + idx_bytes + sp_bytes, cudaMemcpyHostToDevice, st));
         launch_embed<T>(drows, R, tok_emb_, dec_pos_, Ln.x, d, st);
         // head-major KV panels: self [slot][layer][K|V][head][448][64], cross [slot][layer][K|V][head][1536][64]
         const size_t self_head = (size_t)ntc * 64, self_kv = (size_t)ntc * d;
@@ -841,13 +864,6 @@ public:
         const size_t cross_slot = (size_t)Ld * 2 * cross_kv;
         const bool skinny = use_skinny_ && sizeof(T) == 2 && R <= 128 && 4 * d <= 5120;
         if (skinny) {
-            bool distinct = true;   // single-token steps: one row per KV slot
-            {
-                std::vector<int> slots(R);
-                for (int r = 0; r < R; ++r) slots[r] = rows[r].kv_slot;
-                std::sort(slots.begin(), slots.end());
-                distinct = std::adjacent_find(slots.begin(), slots.end()) == slots.end();
-            }
             const bool chain = use_chain_ && cross_mode_ == 2 && fuse_cross_q_;
             const bool proj = use_proj_ && dec_proj_supported(R, d, d) && dec_proj_supported(R, 3 * d, d) && dec_proj_supported(R, 4 * d, d) &&
                               dec_proj_supported(R, d, 4 * d);
@@ -870,14 +886,13 @@ public:
                 mark_begin(Ln.tm, profiling);
                 launch_dec_attention<T>(drows, R, Ln.qkv, d, ck, cv, Ln.att, d, hp_.n_text_head, /*cross=*/1, cross_slot, cross_head, hp_.n_audio_ctx, st);
                 mark_end(Ln.tm, profiling, 2);
-                if (profiling) Ln.cross_bytes += 2.0 * R * hp_.n_audio_ctx * d * sizeof(T);
+                if (profiling) Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T);
                 { Epilogue e; e.bias = L.bco; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.att, d, L.wco, d, Ln.x, d, R, d, d, e, st)) return gemm_fail(); }
                 launch_layernorm<T>(Ln.x, d, L.ln2_g, L.ln2_b, Ln.y, d, R, d, st);
                 { Epilogue e; e.bias = L.b1; e.act = 1; if (!gemm(Ln.y, d, L.w1, d, Ln.h, 4 * d, R, 4 * d, d, e, st)) return gemm_fail(); }
                 { Epilogue e; e.bias = L.b2; e.res = Ln.x; e.res_ld = d; if (!gemm(Ln.h, 4 * d, L.w2, 4 * d, Ln.x, d, R, d, 4 * d, e, st)) return gemm_fail(); }
             }
         }
-        Ln.pend_S = 0;
         if (S > 0) {
             mark_begin(Ln.tm, detail_);
             launch_layernorm_gather<T>(Ln.x, d, didx, dec_ln_g_, dec_ln_b_, Ln.ys, d, S, d, st);
@@ -893,6 +908,56 @@ public:
             CUDA_OK(cudaMemcpyAsync(hp + rows_bytes + idx_bytes + sp_bytes, dres, sizeof(SampleResult) * S, cudaMemcpyDeviceToHost, st));
             if (logits_host)
                 CUDA_OK(cudaMemcpyAsync(logits_host, Ln.logits, sizeof(float) * (size_t)S * hp_.n_vocab, cudaMemcpyDeviceToHost, st));
+        }
+        return true;
+        };   // issue
+
+        bool queued = false;
+        const bool graphable = graph_rows_ > 0 && R <= graph_rows_ && !profiling && !detail_ && !trace_buf_ && !inject && !logits_host;
+        if (graphable && Ln.graph_epoch != pool_epoch_) {   // a KV / cross-KV pool moved since these graphs were captured
+            for (auto& g : Ln.graphs) cudaGraphExecDestroy(g.second.exec);
+            Ln.graphs.clear();
+            Ln.graph_seen.clear();
+            Ln.graph_epoch = pool_epoch_;
+        }
+        if (graphable) {
+            const uint64_t key = ((uint64_t)R << 40) ^ ((uint64_t)S << 24) ^ ((uint64_t)(Ln.cross_seq & 1u) << 20) ^ ((uint64_t)(distinct ? 1 : 0) << 21) ^ (uint64_t)(reinterpret_cast<uintptr_t>(Ln.scratch) >> 4) ^
+                                 ((uint64_t)(reinterpret_cast<uintptr_t>(Ln.pin) >> 4) << 7);
+            auto it = Ln.graphs.find(key);
+            if (it != Ln.graphs.end()) {
+                CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+                count_launches(it->second.n_kernels);
+                Ln.cross_seq += (unsigned)hp_.n_text_layer;
+                queued = true;
+            } else if (++Ln.graph_seen[key] >= 2 && Ln.graphs.size() < 64) {
+                // second time this shape comes by (every first-use cudaFuncSetAttribute has happened): capture it
+                const long k0 = kernel_launch_count();
+                const unsigned seq0 = Ln.cross_seq;
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const bool ok = issue();
+                    cudaGraph_t g = nullptr;
+                    const cudaError_t e1 = cudaStreamEndCapture(st, &g);
+                    cudaGraphExec_t exec = nullptr;
+                    if (ok && e1 == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+                        Ln.graphs[key] = typename Lane::GraphEntry{exec, kernel_launch_count() - k0};
+                        cudaGraphDestroy(g);
+                        CUDA_OK(cudaGraphLaunch(exec, st));
+                        queued = true;
+                    } else {
+                        if (g) cudaGraphDestroy(g);
+                        cudaGetLastError();
+                        Ln.cross_seq = seq0;
+                        graph_rows_ = 0;   // capture is not possible here: direct launches from now on
+                    }
+                } else {
+                    cudaGetLastError();
+                    graph_rows_ = 0;
+                }
+            }
+        }
+        if (!queued && !issue()) return false;
+        Ln.pend_S = 0;
+        if (S > 0) {
             Ln.pend_S = S;
             Ln.pend_off = res_off;
             Ln.pend_pin_off = rows_bytes + idx_bytes + sp_bytes;
@@ -1058,6 +1123,7 @@ private:
         if (pool && old_cap > 0) CUDA_OK(cudaMemcpy(np, pool, (size_t)old_cap * slot_elems * sizeof(P), cudaMemcpyDeviceToDevice));
         if (pool) CUDA_OK(cudaFree(pool));
         pool = np;
+        ++pool_epoch_;   // captured step rounds hold the old pool's address: they are dropped (decode_chunk)
         return true;
     }
     bool grow_audio(int new_cap) {
@@ -1273,6 +1339,7 @@ private:
         // 8-CTA cluster is placed later than single CTAs while another lane's attention CTAs hold every SM.
         use_proj_ = env_int("NOBS_WHISPER_PROJ", 0) != 0 && !f32 && cross_mode_ == 2;
         fc1_fused_ = env_int("NOBS_WHISPER_FC1_FUSED", 1) != 0 && !f32;
+        graph_rows_ = f32 ? 0 : std::max(0, env_int("NOBS_WHISPER_GRAPH_ROWS", 8));
         // The encoder and every decode lane own their activations: a lane may decode while the encoder
         // works on other windows and while other lanes decode.
         auto plan_enc = [&](Arena& a) {
@@ -1369,6 +1436,8 @@ private:
     bool use_skinny_ = true;
     int cross_mode_ = 2;              // bf16 step rows: 2 tcgen05 streaming cross-attention, 1 SIMT streaming (cp.async.bulk ring), 0 block-per-head SIMT
     int cross_ctas_ = 0;              // > 0: cap that kernel's grid
+    unsigned pool_epoch_ = 0;         // bumped whenever a slot pool is reallocated
+    int graph_rows_ = 8;              // step batches of at most this many rows are replayed as CUDA graphs (0: off)
     bool fc1_fused_ = true;           // step batches: FC1 + GELU as one cluster launch instead of split-K GEMM + epilogue kernel
     bool use_proj_ = false;           // step batches: fused cluster projections (split-K reduced in DSMEM, LayerNorm split around the kernel boundary)
     bool use_chain_ = true;           // step batches: projection chains between the attention kernels as single persistent launches

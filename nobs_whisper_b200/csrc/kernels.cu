@@ -20,6 +20,7 @@ bool g_use_pdl = [] { const char* e = getenv("NOBS_WHISPER_PDL"); return !(e && 
 static std::atomic<long> g_launches{0};
 long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void trace_set_kernels(unsigned long long* buf, unsigned int cap) {
     cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));

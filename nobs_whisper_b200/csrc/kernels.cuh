@@ -203,5 +203,6 @@ void trace_set_gemm(unsigned long long* buf, unsigned int cap);
 void trace_set_cross(unsigned long long* buf, unsigned int cap);
 long kernel_launch_count();  // process-wide count of kernels launched through these launchers
 void count_launch();
+void count_launches(long n);   // kernels replayed through a CUDA graph
 
 }  // namespace nobs

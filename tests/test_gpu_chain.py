@@ -17,12 +17,14 @@ pytestmark = pytest.mark.gpu
 
 def make_ctx(nw, path, chain, lanes=None):
     os.environ["NOBS_WHISPER_CHAIN"] = "1" if chain else "0"
+    os.environ["NOBS_WHISPER_FC1_FUSED"] = "0"      # the reference side of this comparison is the split-K GEMM + epilogue pair for every projection
     if lanes is not None:
         os.environ["NOBS_WHISPER_LANES"] = str(lanes)
     try:
         return nw.WhisperContext.new_with_params(path, nw.WhisperContextParameters.default(), precision="bf16")
     finally:
         del os.environ["NOBS_WHISPER_CHAIN"]
+        del os.environ["NOBS_WHISPER_FC1_FUSED"]
         os.environ.pop("NOBS_WHISPER_LANES", None)
 
 

@@ -71,3 +71,39 @@ def test_oracle_agrees_with_the_speculative_ladder(model_dir):
         assert [(s["t0"], s["t1"]) for s in segs] == [(s["t0"], s["t1"]) for s in want]
     orc.close()
     ctx.close()
+
+
+def test_graph_replayed_rounds_change_nothing(model_dir):
+    """Small step batches (single utterances: 1-8 rows) are captured once per shape as a CUDA graph and replayed
+    (csrc/engine.cu decode_chunk).  Same kernels, same arguments: the bf16 result must be bit-identical to direct launches,
+    for one clip at a time (the latency path) and for a small batch, greedy and beam."""
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import ggml_synth, synth_audio
+    path = ggml_synth.ensure_model(model_dir, "tiny", ftype=1)
+    clips = [synth_audio.synth_clip(20 + i, s) for i, s in enumerate([5.0, 30.0, 11.0])]
+
+    def run(graph_rows):
+        os.environ["NOBS_WHISPER_GRAPH_ROWS"] = str(graph_rows)
+        try:
+            ctx = nw.WhisperContext.new_with_params(path, nw.WhisperContextParameters.default(), precision="bf16")
+        finally:
+            del os.environ["NOBS_WHISPER_GRAPH_ROWS"]
+        out = []
+        for beam in (0, 3):
+            p = nw.FullParams.new(nw.SamplingStrategy.BeamSearch(beam_size=beam) if beam else nw.SamplingStrategy.Greedy(best_of=1))
+            p.set_language("en")
+            p.set_no_context(False); p.set_suppress_blank(True); p.set_no_speech_thold(0.6); p.set_entropy_thold(2.4); p.set_logprob_thold(-1.0)
+            for pcm in clips:                      # one utterance per call
+                st = ctx.create_state()
+                assert st.full(p, pcm) == 0
+                out.append(st.segments())
+                st.close()
+            states = [ctx.create_state() for _ in clips]
+            assert nw.full_batch(ctx, states, p, clips) == [0] * len(clips)
+            out.append([st.segments() for st in states])
+            for st in states:
+                st.close()
+        ctx.close()
+        return out
+
+    assert run(8) == run(0)
