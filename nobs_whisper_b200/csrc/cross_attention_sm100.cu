@@ -225,13 +225,16 @@ dec_cross_attention_sm100_kernel(const RowDesc* __restrict__ rows, int n_items, 
 //   registers each and write p as bf16 into one linear row.  Warps 0-3 softmax/output (thread 0 also hands out
 //   items from a device-wide counter), warp 4 TMA producer, warp 5 MMA issuer.  Two CTAs per SM, so that one
 //   streams while the other is in its softmax.
-constexpr int TC_P_BYTES = 4096;         // p of all 1536 keys as one linear bf16 row (3 KB used)
+// p of all 1536 keys for the GM rows of a group: [key / 8][GM][8] bf16 — for GM = 1 one linear row (3 KB used of 4)
+__host__ __device__ constexpr int tc_p_bytes(int gm) { return gm == 1 ? 4096 : 1536 * 2 * gm; }
 constexpr int TC_Q_BYTES = 2 * 2048;     // two q tiles (double buffered across items)
-constexpr int tc_smem_bytes(int stages) { return TC_P_BYTES + TC_Q_BYTES + stages * CA_CHUNK_BYTES + 384 + 1024; }
+__host__ __device__ constexpr int tc_smem_bytes(int stages, int gm = 1) { return tc_p_bytes(gm) + TC_Q_BYTES + stages * CA_CHUNK_BYTES + 384 + 1024; }
 // K-major operand WITHOUT swizzle whose 8x16-byte core matrices overlap at a 16-byte pitch (LBO = 16 B): row 0 of
 // the tile is then a plain linear array; rows 1.. are the bytes that follow (don't-care rows).
-__device__ __forceinline__ uint64_t make_smem_desc_linear_row0(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+// With GM rows per group the rows of a core matrix are real up to row GM - 1: p is stored [key / 8][GM][8 keys], i.e. the core matrix of
+// a key block holds rows 0 .. GM-1 (then whatever follows), and the next key block's core matrix starts GM x 16 bytes later (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_p(uint32_t saddr, uint32_t gm) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)gm << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 constexpr uint32_t TC_IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t TC_IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -248,19 +251,27 @@ __device__ __forceinline__ float tmem_ld_1(uint32_t taddr) {
 // MINB: minimum resident CTAs per SM the register allocation is sized for.  4 caps the kernel at 80 registers (114 without a cap,
 // no spills either way): two of these CTAs then take 30.7 K of the SM's 64 K registers instead of 46 K, which is what lets the
 // projection kernels of TWO other decode lanes (or a kernel and its programmatic successor) be resident beside them.
-template <int TC_STAGES, int SP, int MINB>
+// GM: rows of ONE audio handled per item (1, 2 or 4).  Consecutive rows with the same audio slot (a temperature pass and its speculative
+// successor, the beams of a beam search) attend over the same K / V panels: a group of up to GM of them is one item — their queries fill
+// rows 0 .. g-1 of the 16-row q tile (the score MMA computes those columns anyway), their probabilities rows 0 .. g-1 of the P operand,
+// and the panels are streamed from HBM / L2 into shared memory ONCE for the group.  Needs SP >= GM (score columns c * SP + row).  The
+// groups come from the host (`groups[i]` = first row | size << 24, cross_attention_groups()); an item is then a (group, head) pair.
+template <int TC_STAGES, int SP, int MINB, int GM>
 __global__ void __launch_bounds__(192, MINB)
 dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const RowDesc* __restrict__ rows, int n_items, int n_head,
                               const bf16* __restrict__ q, int ldq, bf16* __restrict__ out, int ldo, long long k_row0, long long v_row0,
-                              long long slot_rows, int n_keys, int* __restrict__ sched, CrossQPartials qp) {
+                              long long slot_rows, int n_keys, int* __restrict__ sched, CrossQPartials qp, const int* __restrict__ groups) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     uint8_t* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);
     constexpr uint32_t TC_TMEM_COLS = SP == 16 ? 256 : 128;
     constexpr uint32_t O_COL = SP == 16 ? 192 : 64;
     constexpr int QD = 4;                             // item queue depth (the scheduler runs two items ahead)
-    uint8_t* sP = smem;                               // [1536] bf16
-    uint8_t* sQ = sP + TC_P_BYTES;                    // [2][2 KB]
+    static_assert(GM == 1 || GM == 2 || GM == 4, "group size");
+    static_assert(SP >= GM, "score blocks of consecutive chunks would overwrite a group row's column");
+    uint8_t* sP = smem;                               // [1536 / 8][GM][8] bf16
+    constexpr int P_BYTES = tc_p_bytes(GM);
+    uint8_t* sQ = sP + P_BYTES;                       // [2][2 KB]
     uint8_t* ring = sQ + TC_Q_BYTES;                  // [TC_STAGES][16 KB]
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + TC_STAGES * CA_CHUNK_BYTES);
     uint64_t* empty = full + TC_STAGES;
@@ -271,14 +282,15 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
     uint64_t* item_full = o_full + 1;                 // QD
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(item_full + QD);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);   // [8]
-    int* item_q = reinterpret_cast<int*>(red + 8);          // [QD]
+    int* item_q = reinterpret_cast<int*>(red + 8);          // [QD]: item | group size << 24, -1 ends the stream
+    float* inv_s = reinterpret_cast<float*>(item_q + QD);   // [4]: 1 / sum of a group row's probabilities
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tr = trace_begin(4, out);
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_kv);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+        mbar_init(&q_full[0], GM == 1 ? 1 : 4); mbar_init(&q_full[1], GM == 1 ? 1 : 4);
         mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
         for (int i = 0; i < QD; ++i) mbar_init(&item_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,8 +317,9 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
             const uint64_t policy = l2_evict_first_policy();
             int stage = 0; uint32_t phase = 0;
             for (int it = 0;; ++it) {
-                const int item = next_item(it);
-                if (item < 0) break;
+                const int packed = next_item(it);
+                if (packed < 0) break;
+                const int item = packed & 0xFFFFFF;
                 const int r = item / n_head, h = item - r * n_head;
                 const long long base = (long long)rows[r].audio_slot * slot_rows + (long long)h * kWinRows;
                 for (int pass = 0; pass < 2; ++pass) {
@@ -350,10 +363,10 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t v_addr = smem_u32(ring + stage * CA_CHUNK_BYTES), p_addr = smem_u32(sP + c * CA_CHUNK_KEYS * 2);
+                    const uint32_t v_addr = smem_u32(ring + stage * CA_CHUNK_BYTES), p_addr = smem_u32(sP + c * CA_CHUNK_KEYS * 2 * GM);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)   // 16 keys per MMA
-                        umma_bf16(tmem_O, make_smem_desc_linear_row0(p_addr + k * 32), make_smem_desc_mnmajor(v_addr + k * 16 * 128),
+                        umma_bf16(tmem_O, make_smem_desc_p(p_addr + k * 32 * GM, GM), make_smem_desc_mnmajor(v_addr + k * 16 * 128),
                                   TC_IDESC_O, (uint32_t)((c | k) != 0));
                     umma_commit(&empty[stage]);
                     if (c == n_chunks - 1) umma_commit(o_full);
@@ -367,17 +380,27 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
         const int row = warp * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         auto fetch = [&](int it) {   // thread 0 only
-            int item = atomicAdd(&sched[0], 1);
+            int item = atomicAdd(&sched[0], 1), g = 1;
             if (item >= n_items) item = -1;
-            item_q[it % QD] = item;
+            else if (GM > 1) {
+                // grouped launch: item = (group, head); the host's group table names the group's first row and its size
+                const int grp = item / n_head, e = __ldg(groups + grp);
+                g = e >> 24;
+                item = (e & 0xFFFFFF) * n_head + (item - grp * n_head);
+            }
+            item_q[it % QD] = item < 0 ? -1 : (item | (g << 24));
             mbar_arrive(&item_full[it % QD]);   // release: the queue entry is visible to whoever completes the wait
         };
-        if (threadIdx.x == 0) { fetch(0); fetch(1); }   // the counter does not depend on the predecessor kernel
+        if (threadIdx.x == 0) { fetch(0); fetch(1); }   // the counter and the row descriptors do not depend on the predecessor kernel
         pdl_wait();   // q does
         trace_end(trace_begin(104, out));
-        auto put_q = [&](int item, int buf) {   // 128 bytes of q -> row 0 of the q tile (row 0 of a swizzle atom is stored linearly)
-            if (warp == 0) {
-                const int r = item / n_head, h = item - r * n_head;
+        // 128 bytes of q per group row -> rows 0 .. g-1 of the q tile (K-major, 128B swizzle: 16-byte chunk j of row i sits at chunk j ^ i;
+        // row 0 is stored linearly).  Warp i writes row i.
+        auto put_q = [&](int packed, int buf) {
+            const int item = packed & 0xFFFFFF, g = GM == 1 ? 1 : packed >> 24;
+            if (warp < g) {
+                const int r = item / n_head + warp, h = item % n_head;
+                uint8_t* qrow = sQ + buf * 2048 + warp * 128;
                 if (qp.partial) {
                     // q is still the split-K partial sums of the query projection: finish it here (fixed split order,
                     // + bias) instead of in a separate epilogue launch; lane -> dims 2*lane, 2*lane + 1
@@ -389,62 +412,79 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
                     }
                     if (qp.bias) { acc.x += __ldg(qp.bias + h * 64 + 2 * lane); acc.y += __ldg(qp.bias + h * 64 + 2 * lane + 1); }
                     const __nv_bfloat162 hv = __floats2bfloat162_rn(acc.x, acc.y);
-                    *reinterpret_cast<__nv_bfloat162*>(sQ + buf * 2048 + lane * 4) = hv;
+                    *reinterpret_cast<__nv_bfloat162*>(qrow + (((lane >> 2) ^ warp) << 4) + (lane & 3) * 4) = hv;
                 } else if (lane < 8) {
                     const uint4 v = *reinterpret_cast<const uint4*>(q + (size_t)r * ldq + h * 64 + lane * 8);
-                    *reinterpret_cast<uint4*>(sQ + buf * 2048 + lane * 16) = v;
+                    *reinterpret_cast<uint4*>(qrow + ((lane ^ warp) << 4)) = v;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            if (GM == 1) {
+                if (warp == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&q_full[buf]); }
+            } else {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&q_full[buf]);
+                if (lane == 0) mbar_arrive(&q_full[buf]);   // one arrival per softmax warp, whether it had a row to write or not
             }
         };
-        int item = next_item(0);
-        if (item >= 0) put_q(item, 0);
-        for (int it = 0; item >= 0; ++it) {
+        int packed = next_item(0);
+        if (packed >= 0) put_q(packed, 0);
+        for (int it = 0; packed >= 0; ++it) {
+            const int item = packed & 0xFFFFFF, g = GM == 1 ? 1 : packed >> 24;
             const int r = item / n_head, h = item - r * n_head;
             mbar_wait(s_full, (uint32_t)(it & 1));
             tc_fence_after();
-            float sv[12];
+            int next = -1;
+#pragma unroll 1
+            for (int gi = 0; gi < g; ++gi) {
+                float sv[12];
 #pragma unroll
-            for (int c = 0; c < 12; ++c) sv[c] = c < n_chunks ? tmem_ld_1(tmem_S + lane_addr + (uint32_t)(c * SP)) : 0.0f;
-            tmem_ld_wait();
-            float lmax = -INFINITY;
+                for (int c = 0; c < 12; ++c) sv[c] = c < n_chunks ? tmem_ld_1(tmem_S + lane_addr + (uint32_t)(c * SP + gi)) : 0.0f;
+                tmem_ld_wait();
+                float lmax = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                sv[c] = (c * CA_CHUNK_KEYS + row < n_keys) ? sv[c] * 0.125f : -INFINITY;
-                lmax = fmaxf(lmax, sv[c]);
+                for (int c = 0; c < 12; ++c) {
+                    sv[c] = (c * CA_CHUNK_KEYS + row < n_keys) ? sv[c] * 0.125f : -INFINITY;
+                    lmax = fmaxf(lmax, sv[c]);
+                }
+                lmax = warp_max(lmax);
+                if (lane == 0) red[warp] = lmax;
+                consumer_sync<128>();
+                const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+                float lsum = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const bf16 pb = __float2bfloat16_rn(expf(sv[c] - mx));   // exp(-inf) = 0 for masked keys
+                    lsum += __bfloat162float(pb);                            // the sum of what the tensor core will see
+                    const int key = c * CA_CHUNK_KEYS + row;
+                    if (c < n_chunks) reinterpret_cast<bf16*>(sP)[((key >> 3) * GM + gi) * 8 + (key & 7)] = pb;
+                }
+                if (gi == g - 1) {
+                    // the last row's probabilities are in: hand P to the tensor core
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(p_full);
+                }
+                lsum = warp_sum(lsum);
+                if (lane == 0) red[4 + warp] = lsum;
+                if (gi == g - 1) {   // use the wait for P * V to prepare the next item
+                    if (threadIdx.x == 0) fetch(it + 2);
+                    next = next_item(it + 1);
+                    if (next >= 0) put_q(next, (it + 1) & 1);
+                }
+                consumer_sync<128>();
+                if (GM > 1 && threadIdx.x == 0) inv_s[gi] = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
             }
-            lmax = warp_max(lmax);
-            if (lane == 0) red[warp] = lmax;
-            consumer_sync<128>();
-            const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-            float lsum = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const bf16 pb = __float2bfloat16_rn(expf(sv[c] - mx));   // exp(-inf) = 0 for masked keys
-                lsum += __bfloat162float(pb);                            // the sum of what the tensor core will see
-                if (c < n_chunks) reinterpret_cast<bf16*>(sP)[c * CA_CHUNK_KEYS + row] = pb;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(p_full);
-            lsum = warp_sum(lsum);
-            if (lane == 0) red[4 + warp] = lsum;
-            if (threadIdx.x == 0) fetch(it + 2);
-            const int next = next_item(it + 1);
-            if (next >= 0) put_q(next, (it + 1) & 1);
-            consumer_sync<128>();
+            if (GM > 1) consumer_sync<128>();   // inv_s is visible to warp 0
             if (warp == 0) {
-                const float inv = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
                 mbar_wait(o_full, (uint32_t)(it & 1));
                 tc_fence_after();
                 uint32_t o0[32], o1[32];
                 tmem_ld_32x32(tmem_O, o0);
                 tmem_ld_32x32(tmem_O + 32, o1);
                 tmem_ld_wait();
-                if (lane == 0) {
-                    bf16* dst = out + (size_t)r * ldo + h * 64;
+                if (lane < g) {   // TMEM lane = group row
+                    const float inv = GM > 1 ? inv_s[lane] : 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
+                    bf16* dst = out + (size_t)(r + lane) * ldo + h * 64;
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
                         uint4 u;
@@ -472,7 +512,7 @@ dec_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_kv, const
             }
             // the next item's first barrier (after its s_full wait) orders warp 0's O read before anyone
             // arrives on the next p_full, i.e. before the next item's P*V can overwrite the accumulator
-            item = next;
+            packed = next;
         }
     }
     tc_fence_before();
@@ -502,32 +542,51 @@ void trace_set_cross(unsigned long long* buf, unsigned int cap) {
 
 namespace {
 int env_or(const char* name, int dflt);
-template <int STAGES, int SP, int MINB>
+template <int STAGES, int SP, int MINB, int GM>
 bool launch_tc(const CUtensorMap& tm, const RowDesc* rows, int n_items, int n_head, const bf16* q, int ldq, bf16* out, int ldo, long long k_row0,
-               long long v_row0, long long slot_rows, int n_keys, int* sched, const CrossQPartials& qp, int grid, cudaStream_t s) {
-    constexpr int SMEM = tc_smem_bytes(STAGES);
+               long long v_row0, long long slot_rows, int n_keys, int* sched, const CrossQPartials& qp, const int* groups, int grid, cudaStream_t s) {
+    constexpr int SMEM = tc_smem_bytes(STAGES, GM);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(dec_cross_attention_tc_kernel<STAGES, SP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(dec_cross_attention_tc_kernel<STAGES, SP, MINB, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
             sm100_set_error("cudaFuncSetAttribute(cross attention tc smem) failed");
             return false;
         }
         configured = true;
     }
-    launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP, MINB>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo, k_row0,
-                  v_row0, slot_rows, n_keys, sched, qp);
+    launch_kernel(dec_cross_attention_tc_kernel<STAGES, SP, MINB, GM>, dim3(grid), dim3(192), (size_t)SMEM, s, true, tm, rows, n_items, n_head, q, ldq, out, ldo,
+                  k_row0, v_row0, slot_rows, n_keys, sched, qp, groups);
     return true;
 }
 }  // namespace
 
+int cross_attention_groups(const RowDesc* rows, int n_rows, int* groups) {
+    // runs of consecutive rows with one audio slot, cut into pieces of at most 4; returns the kernel's group width (1: no row shares a slot
+    // with its neighbour, `groups` is not needed), and leaves the number of groups in groups[n_rows] when the width is 2 or 4
+    int n = 0, width = 1;
+    for (int r = 0; r < n_rows;) {
+        int g = 1;
+        while (g < 4 && r + g < n_rows && rows[r + g].audio_slot == rows[r].audio_slot) ++g;
+        groups[n++] = r | (g << 24);
+        width = g > width ? g : width;
+        r += g;
+    }
+    groups[n_rows] = n;
+    return width <= 2 ? width : 4;
+}
+
 bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
                                          size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s,
-                                         const CrossQPartials* qpart) {
+                                         const CrossQPartials* qpart, const CrossGroups* grp) {
     if (n_rows <= 0) return true;
     const CrossQPartials qp = qpart ? *qpart : CrossQPartials{};
     if ((!q && !qp.partial) || (qp.partial && ((qp.ld & 1) || (qp.plane & 1)))) { sm100_set_error("cross attention (tc): no query"); return false; }
     if (!sched || n_keys <= 0 || n_keys > CA_MAX_KEYS || (ldq % 8) != 0 || (slot_stride % 64) || (k_off % 64) || (v_off % 64) || pool_elems / 64 >= (1ull << 31)) {
         sm100_set_error("cross attention (tc): unsupported shape");
+        return false;
+    }
+    if (grp && grp->width > 1 && (!grp->groups || grp->n_groups <= 0 || grp->n_groups > n_rows || (grp->width != 2 && grp->width != 4))) {
+        sm100_set_error("cross attention (tc): bad row groups");
         return false;
     }
     static int sms = 0, stages = 0, sp = 0, per_sm = 1, low_regs = 1;
@@ -550,7 +609,10 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
         cached_pool = pool;
         cached_elems = pool_elems;
     }
-    const int n_items = n_rows * n_head;
+    // grouped rows: only with the 4-column score pitch and the 80-register build (the default configuration); anything else streams row by row
+    const int gm = (grp && grp->width > 1 && sp == 4 && low_regs && (stages == 2 || stages == 3 || stages == 4)) ? grp->width : 1;
+    const int* groups = gm > 1 ? grp->groups : nullptr;
+    const int n_items = (gm > 1 ? grp->n_groups : n_rows) * n_head;
     int grid = n_items < sms * per_sm ? n_items : sms * per_sm;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     // Balanced waves: 1200 items on 296 CTAs are four full waves plus 16 stragglers, and the launch ends one item time (~10 us of a
@@ -562,10 +624,13 @@ bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const 
         grid = (n_items + waves - 1) / waves;
     }
     bool ok = false;
-#define TC_ARGS tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, qp, grid, s
-#define TC_CASE(S, P) if (stages == S && sp == P) ok = low_regs ? launch_tc<S, P, 4>(TC_ARGS) : launch_tc<S, P, 1>(TC_ARGS); else
+#define TC_ARGS tm, rows, n_items, n_head, q, ldq, out, ldo, (long long)(k_off / 64), (long long)(v_off / 64), (long long)(slot_stride / 64), n_keys, sched, qp, groups, grid, s
+#define TC_CASE(S, P) if (stages == S && sp == P) ok = low_regs ? launch_tc<S, P, 4, 1>(TC_ARGS) : launch_tc<S, P, 1, 1>(TC_ARGS); else
+#define TC_GROUPED(S) if (gm > 1 && stages == S) ok = gm == 2 ? launch_tc<S, 4, 4, 2>(TC_ARGS) : launch_tc<S, 4, 4, 4>(TC_ARGS); else
+    TC_GROUPED(2) TC_GROUPED(3) TC_GROUPED(4)
     TC_CASE(4, 16) TC_CASE(6, 16) TC_CASE(8, 16) TC_CASE(10, 16) TC_CASE(2, 4) TC_CASE(3, 4) TC_CASE(4, 4) TC_CASE(5, 4) TC_CASE(6, 4) TC_CASE(8, 4)
     { sm100_set_error("cross attention (tc): unsupported NOBS_WHISPER_CROSS_STAGES / _SPACING"); return false; }
+#undef TC_GROUPED
 #undef TC_CASE
 #undef TC_ARGS
     if (!ok) return false;

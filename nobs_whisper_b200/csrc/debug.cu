@@ -100,9 +100,23 @@ extern "C" int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_s
     if (!dqf.alloc(q_elems * 4) || !dq.alloc(q_elems * 2) || !dkvf.alloc(2 * kv_elems * 4) || !dkv.alloc(2 * kv_elems * 2) || !dout.alloc(q_elems * 2) ||
         !doutf.alloc(q_elems * 4) || !drows.alloc(sizeof(RowDesc) * R))
         return -2;
+    // streaming 2: row r -> slot r % n_slots (neighbours never share a slot: ungrouped kernel).  streaming 20 + g: row r -> slot
+    // (r / g) % n_slots, i.e. runs of g rows per audio, handed to the tcgen05 kernel as row groups (g up to 4 per item, longer runs are cut).
+    const int run = streaming > 20 ? streaming - 20 : 1;
+    if (streaming > 20) streaming = 2;
     std::vector<RowDesc> hr(R);
-    for (int i = 0; i < R; ++i) hr[i] = RowDesc{0, 0, 0, i % n_slots};
+    for (int i = 0; i < R; ++i) hr[i] = RowDesc{0, 0, 0, (i / run) % n_slots};
     cudaMemcpy(drows.p, hr.data(), sizeof(RowDesc) * R, cudaMemcpyHostToDevice);
+    std::vector<int> hgrp(R + 1);
+    CrossGroups grp;
+    DevBuf dgrp;
+    if (run > 1) {
+        grp.width = cross_attention_groups(hr.data(), R, hgrp.data());
+        grp.n_groups = hgrp[R];
+        if (!dgrp.alloc(sizeof(int) * (R + 1))) return -2;
+        cudaMemcpy(dgrp.p, hgrp.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice);
+        grp.groups = (const int*)dgrp.p;
+    }
     cudaMemcpy(dqf.p, q, q_elems * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dkvf.p, k, kv_elems * 4, cudaMemcpyHostToDevice);
     cudaMemcpy((float*)dkvf.p + kv_elems, v, kv_elems * 4, cudaMemcpyHostToDevice);
@@ -116,7 +130,7 @@ extern "C" int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_s
     bool ok = true;
     if (streaming == 2) {
         ok = launch_dec_cross_attention_tc_sm100((const RowDesc*)drows.p, R, (const bf16*)dq.p, d, dk, 2 * kv_elems, 0, kv_elems, (bf16*)dout.p, d, n_head, slot_stride,
-                                                 n_keys, (int*)dsched.p, 0, s);
+                                                 n_keys, (int*)dsched.p, 0, s, nullptr, run > 1 ? &grp : nullptr);
     } else if (streaming == 1) {
         ok = launch_dec_cross_attention_sm100((const RowDesc*)drows.p, R, (const bf16*)dq.p, d, dk, dv, (bf16*)dout.p, d, n_head, slot_stride, head_stride, n_keys, 0, s);
     } else {

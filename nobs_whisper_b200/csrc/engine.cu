@@ -387,6 +387,7 @@ public:
         std::unordered_map<uint64_t, GraphEntry> graphs;   // captured step rounds by shape (decode_chunk)
         std::unordered_map<uint64_t, int> graph_seen;
         unsigned graph_epoch = 0;
+        CrossGroups cross_grp;                  // row groups of the chunk being queued (device table inside `scratch`)
         int cross_slots = 0;                    // distinct audio slots among the rows of the chunk being queued: rows of one audio (a pass and its
                                                 // speculative successor, beams) stream the same cross-KV panels, which leave HBM once
     };
@@ -557,7 +558,7 @@ public:
                 mark_begin(Ln.tm, timed || detail_);
                 if (!launch_dec_cross_attention_tc_sm100(drows, R, nullptr, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
                                                          (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
-                                                         cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
+                                                         cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp, &Ln.cross_grp))
                     return gemm_fail();
             } else {
                 {   // cross-attention query
@@ -657,7 +658,7 @@ public:
             mark_begin(Ln.tm, timed || detail_);
             if (!launch_dec_cross_attention_tc_sm100(drows, R, qkv, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
                                                      (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), att, d, hp_.n_text_head, cross_slot, hp_.n_audio_ctx,
-                                                     Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st))
+                                                     Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, nullptr, &Ln.cross_grp))
                 return gemm_fail();
             if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             if (!residual(att, d, L.wco, L.bco, L.ln2_g, L.ln2_b)) return false;
@@ -753,7 +754,7 @@ public:
             mark_begin(Ln.tm, timed || detail_);
             if (!launch_dec_cross_attention_tc_sm100(drows, R, nullptr, d, reinterpret_cast<const bf16*>(cross_pool_), (size_t)audio_cap_ * cross_slot,
                                                      (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_), reinterpret_cast<bf16*>(Ln.att), d, hp_.n_text_head,
-                                                     cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp))
+                                                     cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, st, &qp, &Ln.cross_grp))
                 return gemm_fail();
             if (timed) { mark_end(Ln.tm, true, 2); Ln.cross_bytes += 2.0 * Ln.cross_slots * hp_.n_audio_ctx * d * sizeof(T); } else mark_end(Ln.tm, detail_, 13);
             {   // cross out-projection + residual + MLP LayerNorm, FC1 + GELU, FC2 + residual + next LayerNorm, next layer's QKV
@@ -809,7 +810,7 @@ public:
             return true;
         }
         if (!launch_dec_cross_attention_tc_sm100(drows, R, q, ldq, cross_pool_, (size_t)audio_cap_ * cross_slot, (size_t)(ck - cross_pool_), (size_t)(cv - cross_pool_),
-                                                 out, d_, hp_.n_text_head, cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, Ln.stream))
+                                                 out, d_, hp_.n_text_head, cross_slot, hp_.n_audio_ctx, Ln.sched + ((Ln.cross_seq++ & 1u) << 1), cross_ctas_, Ln.stream, nullptr, &Ln.cross_grp))
             return gemm_fail();
         return true;
     }
@@ -825,12 +826,20 @@ public:
             if (rd.token < 0 || rd.token >= hp_.n_vocab || rd.pos < 0 || rd.pos >= ntc || rd.kv_slot < 0 || rd.kv_slot >= kv_cap_ ||
                 rd.audio_slot < 0 || rd.audio_slot >= audio_cap_) { set_err("decode: bad row"); return false; }
         }
-        const size_t rows_bytes = align_up(sizeof(RowDesc) * R, 256), idx_bytes = align_up(sizeof(int) * std::max(S, 1), 256);
+        // staging: rows | row groups of the cross-attention (R + 1 ints) | sample row indices | sampling parameters | results
+        const size_t grp_off = align_up(sizeof(RowDesc) * R, 256);
+        const size_t rows_bytes = grp_off + align_up(sizeof(int) * (R + 1), 256), idx_bytes = align_up(sizeof(int) * std::max(S, 1), 256);
         const size_t sp_bytes = align_up(sizeof(SampleParams) * std::max(S, 1), 256), res_bytes = align_up(sizeof(SampleResult) * std::max(S, 1), 256);
         if (!lane_pin(Ln, rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
         if (!lane_scratch(Ln, rows_bytes + idx_bytes + sp_bytes + res_bytes)) return false;
         char* hp = Ln.pin;
         memcpy(hp, rows, sizeof(RowDesc) * R);
+        {   // rows of one audio that follow each other (a pass and its speculative successor, beams) share their cross-KV panels
+            int* hgrp = reinterpret_cast<int*>(hp + grp_off);
+            Ln.cross_grp = CrossGroups{};
+            const int width = cross_groups_ ? cross_attention_groups(rows, R, hgrp) : 1;
+            if (width > 1) { Ln.cross_grp.groups = reinterpret_cast<const int*>(Ln.scratch + grp_off); Ln.cross_grp.n_groups = hgrp[R]; Ln.cross_grp.width = width; }
+        }
         int* hidx = reinterpret_cast<int*>(hp + rows_bytes);
         for (int i = 0; i < S; ++i) hidx[i] = samp[i] - row_base;
         if (S) memcpy(hp + rows_bytes + idx_bytes, sp, sizeof(SampleParams) * S);
@@ -921,7 +930,7 @@ public:
             Ln.graph_epoch = pool_epoch_;
         }
         if (graphable) {
-            const uint64_t key = ((uint64_t)R << 40) ^ ((uint64_t)S << 24) ^ ((uint64_t)(Ln.cross_seq & 1u) << 20) ^ ((uint64_t)(distinct ? 1 : 0) << 21) ^ (uint64_t)(reinterpret_cast<uintptr_t>(Ln.scratch) >> 4) ^
+            const uint64_t key = ((uint64_t)R << 40) ^ ((uint64_t)Ln.cross_grp.n_groups << 48) ^ ((uint64_t)Ln.cross_grp.width << 56) ^ ((uint64_t)S << 24) ^ ((uint64_t)(Ln.cross_seq & 1u) << 20) ^ ((uint64_t)(distinct ? 1 : 0) << 21) ^ (uint64_t)(reinterpret_cast<uintptr_t>(Ln.scratch) >> 4) ^
                                  ((uint64_t)(reinterpret_cast<uintptr_t>(Ln.pin) >> 4) << 7);
             auto it = Ln.graphs.find(key);
             if (it != Ln.graphs.end()) {
@@ -1324,6 +1333,7 @@ private:
         skinny_logits_ = env_int("NOBS_WHISPER_SKINNY_LOGITS", 1) != 0;
         fuse_qkv_ = env_int("NOBS_WHISPER_FUSE_QKV", 1) != 0;
         cross_ctas_ = env_int("NOBS_WHISPER_CROSS_CTAS", 0);
+        cross_groups_ = env_int("NOBS_WHISPER_CROSS_GROUPS", 1) != 0;
         const int n_lanes = std::min(8, std::max(1, env_int("NOBS_WHISPER_LANES", f32 ? 1 : 2)));
         // with several lanes the step GEMMs run a 2-deep ring (49 KB at 64 rows): two of them fit next to the two
         // attention CTAs (2 x 57 KB) an SM holds for another lane
@@ -1444,6 +1454,7 @@ private:
     int chain_stages_ = 3;
     bool fuse_qkv_ = true;            // single-token steps: the self-attention kernel finishes the QKV projection's split-K sums
     bool skinny_logits_ = true;       // step batches: logits through the swap-AB weight-streaming GEMM
+    bool cross_groups_ = true;        // consecutive rows of one audio are one cross-attention work item (their panels are streamed once)
     bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
     std::mutex enc_mu_, stats_mu_, err_mu_;

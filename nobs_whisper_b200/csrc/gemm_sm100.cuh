@@ -37,9 +37,19 @@ struct CrossQPartials {
     int ld = 0;
     const float* bias = nullptr;
 };
+// Optional: row groups.  Consecutive rows of ONE audio slot (a pass and its speculative successor, the beams of a beam search) attend over
+// the same panels; as a group of up to 4 they are one work item whose panels are streamed once.  cross_attention_groups() (host) cuts the
+// rows into such groups: groups[i] = first row | size << 24, groups[n_rows] = number of groups (the array holds n_rows + 1 ints); it returns
+// the kernel's group width (1 = no neighbours share a slot: pass no groups).  The device copy of the table is what the launch takes.
+struct CrossGroups {
+    const int* groups = nullptr;   // device
+    int n_groups = 0;
+    int width = 1;                 // 1, 2 or 4
+};
+int cross_attention_groups(const RowDesc* rows, int n_rows, int* groups);
 bool launch_dec_cross_attention_tc_sm100(const RowDesc* rows, int n_rows, const bf16* q, int ldq, const bf16* pool, size_t pool_elems, size_t k_off,
                                          size_t v_off, bf16* out, int ldo, int n_head, size_t slot_stride, int n_keys, int* sched, int max_ctas, cudaStream_t s,
-                                         const CrossQPartials* qpart = nullptr);
+                                         const CrossQPartials* qpart = nullptr, const CrossGroups* grp = nullptr);
 // Decoder projection chain (decode_chain_sm100.cu): up to kChainMaxSteps dependent swap-AB split-K projections of one step
 // batch (R <= 128 rows) in ONE persistent launch, separated by device-wide barriers instead of kernel boundaries.  Every
 // step but the last must be reduced (`reduce` = 1: SkinnyEpilogue semantics, identical arithmetic to skinny_reduce_kernel);

@@ -108,11 +108,16 @@ def test_encoder_attention_kernel(n_win, n_head, use_simt):
 
 @pytest.mark.parametrize("R,n_head,n_slots,n_keys,streaming", [(3, 2, 2, 1500, 2), (5, 20, 3, 1500, 2), (130, 6, 4, 1500, 2), (2, 1, 1, 77, 2),
                                                                 (4, 3, 2, 1280, 2), (3, 2, 2, 1500, 1), (130, 6, 4, 1500, 1), (2, 1, 1, 77, 1),
-                                                                (3, 2, 2, 1500, 0)])
+                                                                (3, 2, 2, 1500, 0),
+                                                                (6, 3, 3, 1500, 22), (121, 20, 31, 1500, 22), (7, 2, 2, 1500, 23), (10, 6, 2, 1500, 25),
+                                                                (9, 2, 1, 77, 24), (130, 6, 5, 1280, 24)])
 def test_decoder_cross_attention_kernel(R, n_head, n_slots, n_keys, streaming):
     """Streaming cross-attention kernels (2: tcgen05, 1: SIMT over a cp.async.bulk ring, 0: block-per-head SIMT)
     against a float64 softmax(q K^T / 8) V over head-major panels; more items than SMs, ragged last chunk,
-    rows sharing a slot.  Pad rows past n_keys hold large finite garbage that must not reach the result."""
+    rows sharing a slot.  Pad rows past n_keys hold large finite garbage that must not reach the result.
+    streaming 20 + g: the tcgen05 kernel with ROW GROUPS — runs of g consecutive rows per audio slot (a pass and its speculative
+    successor: 2; beams: 5) are one work item of up to 4 rows whose panels are streamed once; ragged last run, runs longer than 4."""
+    run = streaming - 20 if streaming > 20 else 1
     from nobs_whisper_b200 import _lib
     L = _lib.lib()
     rng = np.random.default_rng(R * 100 + n_head)
@@ -129,9 +134,9 @@ def test_decoder_cross_attention_kernel(R, n_head, n_slots, n_keys, streaming):
     assert np.isfinite(out).all()
     qb, kb, vb = to_bf16(q).astype(np.float64), to_bf16(k[:, :, :n_keys]).astype(np.float64), to_bf16(v[:, :, :n_keys]).astype(np.float64)
     for r in range(R):
-        s_ = r % n_slots
+        s_ = (r // run) % n_slots
         for h in range(n_head):
             sc = kb[s_, h] @ qb[r, h * 64:(h + 1) * 64] * 0.125
             p = np.exp(sc - sc.max())
             ref = (p / p.sum()) @ vb[s_, h]
-            assert np.abs(out[r, h * 64:(h + 1) * 64] - ref).max() < (2e-2 if streaming == 2 else 1e-2) * max(1.0, np.abs(ref).max())
+            assert np.abs(out[r, h * 64:(h + 1) * 64] - ref).max() < (2e-2 if streaming >= 2 else 1e-2) * max(1.0, np.abs(ref).max())
