@@ -10,8 +10,15 @@
 //   max / exp2 / sum in registers (no shuffles), write P_j as bf16 into a 128B-swizzled K-major
 //   tile in shared memory, and fold O_j into a register accumulator with the online-softmax
 //   correction, so TMEM never needs rescaling.
+//
+//   Two builds of the same kernel (template parameter PER_SM):
+//     1: one CTA per SM — S double-buffered in TMEM (512 columns allocated), 3-stage K/V ring, 145 KB of shared memory;
+//     2: two CTAs per SM — S single-buffered (256 columns per CTA), 2-stage ring, 112 KB.  A CTA's softmax threads are a chain of
+//        TMEM round trips and barrier waits (issue slots 44 % active with one CTA); the second CTA's chain fills those gaps.  S_{j+1}
+//        is then issued right behind P_j V_j, i.e. once the softmax threads have read S_j.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -26,19 +33,27 @@ namespace {
 constexpr int AQ = 128;        // queries per CTA
 constexpr int AK = 128;        // keys per block
 constexpr int DH = 64;         // head size
-constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * DH * 2;  // 16 KB: Q, K, V tiles and each 64-key half of P
-constexpr int ATT_SMEM = TILE_BYTES /*Q*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
-constexpr uint32_t TMEM_COLS_ATT = 512;   // S: 2 x 128, O: 2 x 64 (384 used)
+// PER_SM = 2 has no alignment slack: two CTAs (2 x (112.25 KB + 1 KB reserved)) just fit the SM's 228 KB; the kernel checks the
+// 1024-byte alignment the swizzled tiles need (a dynamic segment with no static shared memory in front of it starts aligned).
+__host__ __device__ constexpr int att_kv_stages(int per_sm) { return per_sm == 1 ? 3 : 2; }
+__host__ __device__ constexpr int att_smem(int per_sm) {
+    return TILE_BYTES /*Q*/ + att_kv_stages(per_sm) * 2 * TILE_BYTES /*K,V*/ + 2 * TILE_BYTES /*P*/ + (per_sm == 1 ? 1024 : 0) + 256;
+}
 
 // instruction descriptors (kind::f16, D fp32, A/B bf16): S = Q K^T both K-major; O = P V with B MN-major
 constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AK >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
 constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DH >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
 
-__global__ void __launch_bounds__(192, 1)
+template <int PER_SM>
+__global__ void __launch_bounds__(192, PER_SM)
 enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int d, int n_valid) {
-    extern __shared__ uint8_t smem_raw[];
+    constexpr int KV_STAGES = att_kv_stages(PER_SM);
+    constexpr uint32_t TMEM_COLS_ATT = PER_SM == 1 ? 512 : 256;   // S: 2 x 128 (or 1 x 128), O: 2 x 64
+    constexpr int S_BUFS = PER_SM == 1 ? 2 : 1;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
+    if (PER_SM != 1 && (raw & 1023u)) __trap();   // no slack to align with
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;                        // [stage][16 KB]
@@ -71,8 +86,8 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;          // columns [0, 256)
-    const uint32_t tmem_O = tmem_base + 256;    // columns [256, 384)
+    const uint32_t tmem_S = tmem_base;                 // columns [0, 128 * S_BUFS)
+    const uint32_t tmem_O = tmem_base + S_BUFS * AK;   // 2 x 64 columns
 
     if (warp == 4) {
         // ===== TMA producer: Q once, then K/V blocks through the ring =====
@@ -102,17 +117,17 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
                 const uint32_t k_addr = smem_u32(sK + stage * TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    umma_bf16(tmem_S + (uint32_t)((j & 1) * AK), make_smem_desc_kmajor(q_addr + k * 32), make_smem_desc_kmajor(k_addr + k * 32), IDESC_S,
+                    umma_bf16(tmem_S + (uint32_t)((j % S_BUFS) * AK), make_smem_desc_kmajor(q_addr + k * 32), make_smem_desc_kmajor(k_addr + k * 32), IDESC_S,
                               (uint32_t)(k != 0));
-                umma_commit(&s_full[j & 1]);
+                umma_commit(&s_full[j % S_BUFS]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_S(0);
-        if (n_blk > 1) issue_S(1);
+        if (S_BUFS == 2 && n_blk > 1) issue_S(1);
         for (int j = 0; j < n_blk; ++j) {
-            mbar_wait(p_full, (uint32_t)(j & 1));   // P_j is in smem; S buffer j % 2 has been read
+            mbar_wait(p_full, (uint32_t)(j & 1));   // P_j is in smem; the S buffer of block j has been read
             tc_fence_after();
             const int stage = j % KV_STAGES;
             if (lane == 0) {
@@ -125,7 +140,7 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
                 umma_commit(&kv_empty[stage]);    // K_j / V_j consumed
             }
             __syncwarp();
-            if (j + 2 < n_blk) issue_S(j + 2);
+            if (j + S_BUFS < n_blk) issue_S(j + S_BUFS);
         }
     } else {
         // ===== softmax + output: thread = one query row =====
@@ -141,7 +156,7 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
         uint8_t* p_row = sP + row * 128;
         const int sw = row & 7;
         for (int j = 0; j < n_blk; ++j) {
-            mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+            mbar_wait(&s_full[j % S_BUFS], (uint32_t)((j / S_BUFS) & 1));
             tc_fence_after();
             // pass 1: row maximum of this block
             float bmax = -INFINITY;
@@ -149,7 +164,7 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
 #pragma unroll 1
             for (int c0 = 0; c0 < AK; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_S + lane_addr + (uint32_t)((j & 1) * AK + c0), v);
+                tmem_ld_32x32(tmem_S + lane_addr + (uint32_t)((j % S_BUFS) * AK + c0), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -176,7 +191,7 @@ enc_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* _
 #pragma unroll 1
             for (int c0 = 0; c0 < AK; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_S + lane_addr + (uint32_t)((j & 1) * AK + c0), v);
+                tmem_ld_32x32(tmem_S + lane_addr + (uint32_t)((j % S_BUFS) * AK + c0), v);
                 tmem_ld_wait();
                 uint32_t packed[16];
 #pragma unroll
@@ -246,17 +261,25 @@ bool launch_enc_attention_bf16_sm100(const bf16* qkv, bf16* out, int n_win, int 
     CUtensorMap tm;
     // the whole qkv matrix [n_win*1536][3d]; one map serves Q, K and V tiles (64 columns x 128 rows)
     if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)3 * d, (uint64_t)n_win * kWinRows, (uint64_t)3 * d, 64, 128)) return false;
+    // NOBS_WHISPER_ENC_ATT_PER_SM: 2 (default) = two CTAs per SM with a single S buffer each, 1 = one CTA per SM with S double-buffered
+    static const int per_sm = [] { const char* v = getenv("NOBS_WHISPER_ENC_ATT_PER_SM"); return (v && *v == '1') ? 1 : 2; }();
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(enc_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(enc_attention_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem(1)) != cudaSuccess ||
+            cudaFuncSetAttribute(enc_attention_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem(2)) != cudaSuccess) {
             sm100_set_error("cudaFuncSetAttribute(attention smem) failed");
             return false;
         }
         configured = true;
     }
     dim3 grid(kWinRows / AQ, n_head, n_win);
-    prefer_max_shared_carveout(reinterpret_cast<const void*>(&enc_attention_sm100_kernel));
-    enc_attention_sm100_kernel<<<grid, 192, ATT_SMEM, s>>>(tm, out, d, 1500);
+    if (per_sm == 1) {
+        prefer_max_shared_carveout(reinterpret_cast<const void*>(&enc_attention_sm100_kernel<1>));
+        enc_attention_sm100_kernel<1><<<grid, 192, att_smem(1), s>>>(tm, out, d, 1500);
+    } else {
+        prefer_max_shared_carveout(reinterpret_cast<const void*>(&enc_attention_sm100_kernel<2>));
+        enc_attention_sm100_kernel<2><<<grid, 192, att_smem(2), s>>>(tm, out, d, 1500);
+    }
     count_launch();
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { sm100_set_error(std::string("attention launch: ") + cudaGetErrorString(err)); return false; }

@@ -84,6 +84,9 @@ public:
         if (encout_pool_) cudaFree(encout_pool_);
         if (pcm_dev_) cudaFree(pcm_dev_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        for (auto& t : enc_ring_) { if (t.begin) cudaEventDestroy(t.begin); if (t.end) cudaEventDestroy(t.end); }
+        for (auto& e : enc_pin_ev_) if (e) cudaEventDestroy(e);
+        if (enc_pin_) cudaFreeHost(enc_pin_);
         if (env_int("NOBS_WHISPER_PROFILE_HOST", 0))
             fprintf(stderr, "[nobs profile] decode host: issuing launches %.1f ms, waiting for the GPU %.1f ms\n", host_issue_ms_, host_wait_ms_);
         if (detail_) {
@@ -235,23 +238,66 @@ public:
     // ------------------------------------------------------------------ K2-K4
     // Lanes may be driven by one host thread each (full.cpp): the encoder (one stream, one set of activations) is taken by one
     // thread at a time, while the other lanes keep decoding.
-    bool encode(const std::vector<EncodeRequest>& reqs) override {
+    // encode_async queues the windows on the encoder stream and returns a ticket; encode_wait blocks the calling thread until the
+    // ticket's encoder output and cross-KV panels are complete.  A lane that has other audios to decode keeps decoding them while
+    // the windows of the audios that became due are encoded (full.cpp), instead of standing still for the ~10 ms a window takes.
+    bool encode_async(const std::vector<EncodeRequest>& reqs, long* ticket) override {
         std::lock_guard<std::mutex> enc_lock(enc_mu_);
         CUDA_OK(cudaSetDevice(device_));
-        CUDA_OK(cudaEventRecord(ev_[0], stream_));
-        for (size_t b0 = 0; b0 < reqs.size(); b0 += enc_batch_) {
-            const int nb = (int)std::min<size_t>(enc_batch_, reqs.size() - b0);
-            if (!encode_batch(&reqs[b0], nb)) return false;
+        const long seq = enc_issued_ + 1;
+        EncTicket& t = enc_ring_[seq % kEncRing];
+        if (t.seq > 0 && !t.counted) {   // the ring slot's previous ticket (kEncRing calls ago) has to be complete before its events are re-recorded
+            CUDA_OK(cudaEventSynchronize(t.end));
+            account_ticket(t);
         }
-        CUDA_OK(cudaEventRecord(ev_[1], stream_));
-        CUDA_OK(cudaStreamSynchronize(stream_));
+        if (!t.begin) { CUDA_OK(cudaEventCreate(&t.begin)); CUDA_OK(cudaEventCreate(&t.end)); }
+        CUDA_OK(cudaEventRecord(t.begin, stream_));
+        bool ok = true;
+        for (size_t b0 = 0; ok && b0 < reqs.size(); b0 += enc_batch_) {
+            const int nb = (int)std::min<size_t>(enc_batch_, reqs.size() - b0);
+            ok = encode_batch(&reqs[b0], nb);
+        }
+        CUDA_OK(cudaEventRecord(t.end, stream_));
+        t.seq = seq; t.counted = false;
+        enc_issued_ = seq;
+        *ticket = seq;
+        return ok;
+    }
+    bool encode_wait(long ticket) override {
+        cudaEvent_t ev = nullptr;
+        {
+            std::lock_guard<std::mutex> enc_lock(enc_mu_);
+            if (ticket <= enc_done_ || ticket > enc_issued_) return ticket <= enc_done_;
+            const EncTicket& t = enc_ring_[ticket % kEncRing];
+            if (t.seq == ticket) ev = t.end;   // else: the slot was recycled, which only happens after its ticket completed
+        }
+        CUDA_OK(cudaSetDevice(device_));
+        if (ev) CUDA_OK(cudaEventSynchronize(ev));   // outside the lock: other lanes may queue their windows meanwhile
+        std::lock_guard<std::mutex> enc_lock(enc_mu_);
+        for (long q = enc_done_ + 1; q <= ticket; ++q) {   // the stream is in order: everything up to the ticket is complete
+            EncTicket& t = enc_ring_[q % kEncRing];
+            if (t.seq == q && !t.counted) account_ticket(t);
+        }
+        if (ticket > enc_done_) enc_done_ = ticket;
+        if (enc_done_ == enc_issued_) {   // nothing queued behind it: every timing mark of the stream is complete
+            std::lock_guard<std::mutex> stats_lock(stats_mu_);
+            collect_marks();
+        }
         CUDA_OK(cudaGetLastError());
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
-        std::lock_guard<std::mutex> stats_lock(stats_mu_);
-        stats.ms_encode += ms;
-        collect_marks();
         return true;
+    }
+    struct EncTicket {
+        cudaEvent_t begin = nullptr, end = nullptr;
+        long seq = 0;
+        bool counted = true;
+    };
+    void account_ticket(EncTicket& t) {   // enc_mu_ held, t.end complete
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.begin, t.end) == cudaSuccess) {
+            std::lock_guard<std::mutex> stats_lock(stats_mu_);
+            stats.ms_encode += ms;
+        }
+        t.counted = true;
     }
 
     // ---- per-launch event timing (profiling mode); one context per stream
@@ -300,9 +346,15 @@ public:
     bool encode_batch(const EncodeRequest* reqs, int nb) {
         const int d = d_, nm = hp_.n_mels, M = nb * kWinRows;
         // window descriptors
-        if (!ensure_pin(sizeof(PackJob) * nb)) return false;
-        CUDA_OK(cudaStreamSynchronize(stream_));  // pinned staging is reused across batches
-        PackJob* pj = reinterpret_cast<PackJob*>(pin_);
+        // window descriptors travel through a ring of pinned tables: a table is rewritten only after the copy that read it has completed
+        // (an event per table), so queueing a batch never waits for the encoder stream to drain
+        if (!enc_pin_) {
+            CUDA_OK(cudaMallocHost(&enc_pin_, sizeof(PackJob) * (size_t)enc_batch_ * kEncPin));
+            for (auto& e : enc_pin_ev_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const int pslot = (int)(enc_pin_next_++ % kEncPin);
+        if (enc_pin_next_ > kEncPin) CUDA_OK(cudaEventSynchronize(enc_pin_ev_[pslot]));
+        PackJob* pj = enc_pin_ + (size_t)pslot * enc_batch_;
         for (int w = 0; w < nb; ++w) {
             const DeviceMel& m = *reqs[w].mel;
             if (!m.raw || reqs[w].audio_slot < 0 || reqs[w].audio_slot >= audio_cap_) { set_err("encode: bad request"); return false; }
@@ -310,6 +362,7 @@ public:
         }
         if (!ensure_dev_scratch(sizeof(PackJob) * nb)) return false;
         CUDA_OK(cudaMemcpyAsync(dev_scratch_, pj, sizeof(PackJob) * nb, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaEventRecord(enc_pin_ev_[pslot], stream_));
         if (!rezero_conv_pads(nb)) return false;
         launch_pack_mel<T>(reinterpret_cast<const PackJob*>(dev_scratch_), nb, nm, e_mel_, stream_);
         // conv1: rows (w, t) read the 3 neighbouring mel frames in place (row stride n_mels, K = 3*n_mels)
@@ -1391,7 +1444,12 @@ private:
         plan_enc(a);
         for (auto& L : lanes_) {
             plan_dec(a, L);
-            CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            {   // NOBS_WHISPER_DEC_PRIORITY=1: the lanes' (latency-bound) kernels are placed before pending encoder CTAs
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                if (env_int("NOBS_WHISPER_DEC_PRIORITY", 0) && hi < lo) CUDA_OK(cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, hi));
+                else CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            }
             for (auto& e : L.ev) CUDA_OK(cudaEventCreate(&e));
             L.tm.s = L.stream;
         }
@@ -1458,6 +1516,12 @@ private:
     bool fuse_cross_q_ = true;        // the tcgen05 cross-attention sums the query projection's split-K partials itself
     bool detail_ = false;             // NOBS_WHISPER_PROFILE_DECODE=1: per-kernel-class event timing of decoder steps
     std::mutex enc_mu_, stats_mu_, err_mu_;
+    static constexpr int kEncRing = 64, kEncPin = 16;
+    EncTicket enc_ring_[kEncRing];
+    long enc_issued_ = 0, enc_done_ = 0;      // tickets handed out / known complete (enc_mu_)
+    PackJob* enc_pin_ = nullptr;              // kEncPin tables of enc_batch_ window descriptors
+    cudaEvent_t enc_pin_ev_[kEncPin] = {};
+    unsigned long enc_pin_next_ = 0;
     void set_err(const std::string& e, bool keep_first = false) {
         std::lock_guard<std::mutex> lock(err_mu_);
         if (!keep_first || err_.empty()) err_ = e;

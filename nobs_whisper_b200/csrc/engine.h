@@ -79,7 +79,15 @@ public:
     virtual void free_mel(DeviceMel& m) = 0;
 
     virtual bool compute_mel(const std::vector<MelRequest>& reqs) = 0;
-    virtual bool encode(const std::vector<EncodeRequest>& reqs) = 0;
+    // The encoder has its own stream.  encode_async queues the windows and returns a ticket, encode_wait blocks until the ticket's
+    // encoder output and cross-KV panels are complete (tickets complete in the order they were handed out).
+    virtual bool encode_async(const std::vector<EncodeRequest>& reqs, long* ticket) = 0;
+    virtual bool encode_wait(long ticket) = 0;
+    bool encode(const std::vector<EncodeRequest>& reqs) {
+        long ticket = 0;
+        const bool queued = encode_async(reqs, &ticket);
+        return encode_wait(ticket) && queued;
+    }
     // Decode lanes: independent (stream, workspace) pairs.  Jobs are partitioned over lanes by the host driver;
     // while one lane streams its cross-KV panels (HBM-bound) the projection chain of another lane
     // (latency-bound) runs on the same SMs, and the host prepares one lane's next round while the others compute.

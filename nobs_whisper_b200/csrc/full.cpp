@@ -75,6 +75,10 @@ struct Job {
     // bookkeeping of the round in flight
     int first_sample = -1, n_samples = 0;
     std::vector<int> live;  // decoder index of each sample of this round
+    // the window this audio is about to decode is still with the encoder: it joins the lane's rounds again at round enc_round
+    bool enc_wait = false;
+    long enc_ticket = 0;
+    long enc_round = 0;
     bool speculate = false; // this audio may run a shadow pass (greedy, best_of 1, pass 0 is argmax, a fallback temperature exists)
     Shadow sh;
 };
@@ -130,6 +134,8 @@ class Driver {
         std::vector<float> inject;             // scripted-logits test hook: replacement logits per sample of the round
         std::vector<unsigned char> inject_mask;
         bool inflight = false;
+        long round = 0;                        // rounds queued on this lane so far
+        bool stalled = false;                  // the last turn found no rows to decode: wait for every window that is with the encoder
     };
 
 public:
@@ -258,12 +264,14 @@ private:
                 if (!eng_.decode_submit(ln, L.rows, L.samp, L.sp, nullptr, scripted ? L.inject.data() : nullptr, scripted ? L.inject_mask.data() : nullptr))
                     return -8;
                 L.inflight = true;
+                L.round++;
                 active = true;
                 return 0;
             }
             bool pending = false;
-            for (int i : L.jobs) pending |= (jobs_[i].phase == Phase::Window);
-            if (!pending) return 0;  // otherwise: windows that still have to be encoded
+            for (int i : L.jobs) pending |= (jobs_[i].phase == Phase::Window) || jobs_[i].enc_wait;
+            if (!pending) return 0;  // otherwise: windows that still have to be encoded, or are with the encoder
+            L.stalled = true;
         }
     }
 
@@ -277,6 +285,7 @@ private:
             eng_.decode_collect((int)ln, dropped);
             lanes_[ln].inflight = false;
         }
+        for (Job& j : jobs_) if (j.enc_wait) { eng_.encode_wait(j.enc_ticket); j.enc_wait = false; }   // the encoder reads the states' mel buffers
         set_last_error(first_error);
         for (int i = 0; i < n; ++i) rc[i] = (jobs_.size() > (size_t)i && jobs_[i].rc != 0) ? jobs_[i].rc : code;
         return code;
@@ -375,10 +384,16 @@ private:
         return true;
     }
 
-    // Encode every window that is due (language-detect windows included), as one batch.
+    // Encode every window that is due (language-detect windows included), as one batch.  The batch is queued on the encoder's own
+    // stream; the lane does not stand still for it: audios that have rows keep decoding, and an audio whose window is with the
+    // encoder joins again a fixed number of rounds later (kEncDelay; by then the ~10 ms a window takes have normally passed, and
+    // if not the lane waits).  The join round depends on the audios' states only, never on timing, so rounds are composed the same
+    // way in every run.  When no audio of the lane has rows (the first windows of a batch), the lane waits for the encoder at once.
     bool encode_round(LaneState& L) {
+        static const int delay = [] { const char* v = getenv("NOBS_WHISPER_ENC_DELAY"); return (v && *v) ? std::max(0, atoi(v)) : 3; }();
         std::vector<EncodeRequest>& enc_ = L.enc;
         enc_.clear();
+        std::vector<Job*> queued;
         for (int ji : L.jobs) {
             Job& j = jobs_[ji];
             if (j.phase == Phase::Window && j.seek + kDeltaMin >= j.seek_end) j.phase = Phase::Finished;  // under 100 ms left
@@ -388,15 +403,35 @@ private:
                 enc_.push_back(EncodeRequest{&j.st->mel, seek, j.st->audio_slot});
                 j.st->encoded_seek = seek;
                 j.st->stats.n_windows++;
+                queued.push_back(&j);
             }
-            if (j.phase == Phase::Window) {
+        }
+        if (!enc_.empty()) {
+            long ticket = 0;
+            const bool ok = eng_.encode_async(enc_, &ticket);
+            for (Job* j : queued) { j->enc_wait = true; j->enc_ticket = ticket; j->enc_round = L.round + delay; }
+            if (!ok) return false;
+        }
+        bool others_have_rows = false;
+        for (int ji : L.jobs) {
+            const Job& j = jobs_[ji];
+            others_have_rows |= !j.enc_wait && (j.phase == Phase::Prefill || j.phase == Phase::Step);
+        }
+        for (int ji : L.jobs) {
+            Job& j = jobs_[ji];
+            if (j.enc_wait && (delay == 0 || L.stalled || !others_have_rows || L.round >= j.enc_round)) {
+                if (!eng_.encode_wait(j.enc_ticket)) return false;
+                j.enc_wait = false;
+            }
+            if (j.phase == Phase::Window && !j.enc_wait) {
                 if (j.seek > j.seek_start && j.seek + 500 >= j.seek_end) j.st->prompt_past.clear();
                 j.it = 0;
                 j.best = 0;
                 j.phase = Phase::Prefill;
             }
         }
-        return enc_.empty() || eng_.encode(enc_);
+        L.stalled = false;
+        return true;
     }
 
     void fill_sample_params(const Job& j, const Dec& d, float t_cur, bool prefill, int decoder_idx, SampleParams& sp) {
@@ -446,6 +481,7 @@ private:
         j.n_samples = 0;
         j.live.clear();
         whisper_state* st = j.st;
+        if (j.enc_wait) return false;   // its window is still with the encoder (encode_round)
         if (j.phase == Phase::LangDetect) {
             rows_.push_back(RowDesc{vocab_.token_sot, 0, st->kv_slots[0], st->audio_slot});
             samp_.push_back((int)rows_.size() - 1);
