@@ -161,6 +161,39 @@ def turbo_latency(n_clips: int):
             "timing": "host wall clock around WhisperEngine.transcribe (H2D of the PCM and D2H of the text included)"}
 
 
+def beam5_latency(n_clips: int):
+    """BASELINE.json configs[1]: whisper base, beam_size 5 with an initial_prompt custom vocabulary, one 30-s window per call
+    (whisper-rs shaped API: FullParams BeamSearch + set_initial_prompt); wall clock per window.  The five beams of a window share one
+    audio slot, so the tcgen05 cross-attention streams their K / V panels once per group of up to four rows."""
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import ggml_synth, synth_audio
+    vocab = ("Claude Code, Anthropic, Supabase, Vercel, shadcn, tRPC, Drizzle, Zod, pnpm, Bun, Deno, Turso, Neon, PlanetScale, Turborepo, Tauri, "
+             "SvelteKit, Nuxt, Astro, Vite, Zustand, TanStack, LangChain, LlamaIndex, Ollama, Cursor, Neovim, Vitest, Playwright, Prisma")
+    ctx = nw.WhisperContext.new_with_params(ggml_synth.ensure_model(MODEL_DIR, "base", ftype=1, init="fanin"), nw.WhisperContextParameters.default(),
+                                            precision="bf16")
+    ms, rows = [], 0
+    for i in range(n_clips + 2):
+        pcm = synth_audio.synth_clip(7000 + i, WINDOW_S)
+        p = nw.FullParams.new(nw.SamplingStrategy.BeamSearch(beam_size=5))
+        p.set_language("en")
+        p.set_initial_prompt(vocab)
+        p.set_no_context(False); p.set_suppress_blank(True); p.set_no_speech_thold(0.6); p.set_entropy_thold(2.4); p.set_logprob_thold(-1.0)
+        st = ctx.create_state()
+        t0 = time.perf_counter()
+        st.full(p, pcm)
+        n_seg = len(st.segments())
+        dt = 1e3 * (time.perf_counter() - t0)
+        if i >= 2:   # two warm-up windows
+            ms.append(dt)
+            rows += n_seg
+        st.close()
+    ctx.close()
+    return {"workload": "whisper base bf16, beam_size 5 + initial_prompt custom vocabulary (130 prompt tokens), one 30-s synthetic window per call, "
+                        "temperature fallback as the reference inherits it",
+            "n": len(ms), "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)), "mean_ms": float(np.mean(ms)),
+            "segments": int(rows), "timing": "host wall clock around WhisperState.full + segment read-back (H2D of the PCM and D2H of the text included)"}
+
+
 def run_reference(args, rank, world, arch_name):
     """--impl reference: the oracle port on the host cores, bounded sample per step."""
     if rank != 0:
@@ -227,6 +260,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: stop starting new timed steps once this much wall time is spent")
     ap.add_argument("--no-cpu-4threads", action="store_true", help="skip the second cpu_baseline pass at the upstream default of 4 threads")
     ap.add_argument("--latency-clips", type=int, default=200, help="5-s utterances for the large-v3-turbo latency figure (0: skip); BASELINE config 5 asks for >= 200")
+    ap.add_argument("--beam-clips", type=int, default=20, help="30-s windows for the base / beam 5 / vocabulary-prompt latency figure of BASELINE config 2 (0: skip)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU transcribes its own --windows windows; strong: --windows windows in total (BASELINE config 4: one hour = 120 windows), "
                          "rank r takes shard_range(windows, world, r)")
@@ -418,6 +452,12 @@ def main():
         latency = None
         if args.latency_clips > 0 and world == 1:
             latency = turbo_latency(args.latency_clips)
+        latency_beam5 = None
+        if args.beam_clips > 0 and world == 1:
+            try:
+                latency_beam5 = beam5_latency(args.beam_clips)
+            except Exception as exc:  # auxiliary figure: never lose the headline line to it
+                latency_beam5 = {"error": str(exc)}
         line = {
             "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -445,6 +485,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "latency": latency,
+            "latency_beam5": latency_beam5,
         }
         print(json.dumps(line, default=float), flush=True)
     eng.close()

@@ -68,3 +68,47 @@ def test_bf16_lanes_are_deterministic_and_well_formed(model_dir):
         assert 0 <= lang < 100
         for s in segs:
             assert s["t0"] <= s["t1"]
+
+
+def test_sample_budget_cut_inside_a_shared_prompt_row(model_dir):
+    """A lane round whose samples exceed the engine's per-chunk sample budget is cut into chunks; with best_of / beam_size > 1 the
+    prompt's last row is sampled n times, and the cut must never separate such a row from the samples that refer to it
+    (engine.cu decode_submit).  NOBS_WHISPER_DEC_SAMPLES=8 forces the cut into every round of a 6-audio batch with 5 decoders each;
+    in the fp32 parity mode the result must be bit-identical to the unconstrained engine."""
+    import nobs_whisper_b200 as nw
+    from nobs_whisper_b200 import ggml_synth, synth_audio
+    path = ggml_synth.ensure_model(model_dir, "micro", init="fanin")
+    clips = [synth_audio.synth_clip(300 + i, s) for i, s in enumerate([30.0, 9.0, 30.0, 17.0, 4.0, 30.0])]
+
+    def run(budget, **kw):
+        if budget:
+            os.environ["NOBS_WHISPER_DEC_SAMPLES"] = str(budget)
+        try:
+            return run_batch(nw, path, "fp32", 1, clips, **kw)
+        finally:
+            os.environ.pop("NOBS_WHISPER_DEC_SAMPLES", None)
+
+    for kw in (dict(beam=5), dict(beam=5, prompt="Claude Code, Anthropic")):
+        assert run(8, **kw) == run(0, **kw)
+
+    # greedy with best_of 5 at a sampling temperature: five decoders draw their first token from the one prompt row
+    def run_best_of(budget):
+        if budget:
+            os.environ["NOBS_WHISPER_DEC_SAMPLES"] = str(budget)
+        try:
+            ctx = nw.WhisperContext.new_with_params(path, nw.WhisperContextParameters.default(), precision="fp32")
+        finally:
+            os.environ.pop("NOBS_WHISPER_DEC_SAMPLES", None)
+        p = nw.FullParams.new(nw.SamplingStrategy.Greedy(best_of=5))
+        p.set_language("en")
+        p.set_temperature(0.4)
+        p.set_no_context(False); p.set_suppress_blank(True); p.set_no_speech_thold(0.6); p.set_entropy_thold(2.4); p.set_logprob_thold(-1.0)
+        states = [ctx.create_state() for _ in clips]
+        assert nw.full_batch(ctx, states, p, clips) == [0] * len(clips)
+        out = [st.segments() for st in states]
+        for st in states:
+            st.close()
+        ctx.close()
+        return out
+
+    assert run_best_of(8) == run_best_of(0)
