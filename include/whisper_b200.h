@@ -379,6 +379,12 @@ int whisper_b200_debug_enc_attention(int n_win, int n_head, const float* qkv, fl
  * 0 = block-per-head SIMT kernel. */
 int whisper_b200_debug_dec_cross_attention(int R, int n_head, int n_slots, int n_keys, const float* q, const float* k, const float* v, float* out,
                                            int streaming);
+/* streaming 20 + g (g = 2..9): the tcgen05 kernel with ROW GROUPS — row r uses slot (r / g) % n_slots, i.e. runs of g consecutive rows per
+ * audio; a run is cut into work items of up to 4 rows whose K / V panels are streamed once.
+ * Host-only hook (no GPU needed): the grouping itself.  audio_slots[n_rows] -> groups[i] = first row | size << 24 for i < the number of
+ * groups, which is left in groups[n_rows] (the array holds n_rows + 1 ints).  Returns the kernel's group width: 1 (no two neighbours share
+ * a slot), 2 or 4. */
+int whisper_b200_debug_cross_groups(const int* audio_slots, int n_rows, int* groups);
 
 /* Micro-benchmark hook: average device microseconds per launch of the decoder-step kernels for R token
  * rows at model width d (see csrc/debug.cu for the index meaning of out_us[0..12]; out_us holds 16 floats). */

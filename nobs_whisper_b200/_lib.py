@@ -227,6 +227,7 @@ SIGNATURES = {
     "whisper_b200_set_profiling": (None, [vp, C.c_int]),
     "whisper_b200_debug_enc_attention": (C.c_int, [C.c_int, C.c_int, fp, fp, C.c_int]),
     "whisper_b200_debug_dec_cross_attention": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, C.c_int]),
+    "whisper_b200_debug_cross_groups": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "whisper_b200_debug_time_decode_kernels": (C.c_int, [C.c_int, C.c_int, C.c_int, fp]),
     "whisper_b200_debug_dec_proj": (C.c_int, [C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int, fp, fp, fp, fp, fp, fp, C.c_int, fp]),
     "whisper_b200_debug_grid_sync": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp]),

@@ -85,6 +85,13 @@ extern "C" int whisper_b200_debug_enc_attention(int n_win, int n_head, const flo
     return 0;
 }
 
+extern "C" int whisper_b200_debug_cross_groups(const int* audio_slots, int n_rows, int* groups) {
+    if (!audio_slots || !groups || n_rows <= 0) return -1;
+    std::vector<RowDesc> rows(n_rows);
+    for (int i = 0; i < n_rows; ++i) rows[i] = RowDesc{0, 0, 0, audio_slots[i]};
+    return cross_attention_groups(rows.data(), n_rows, groups);
+}
+
 // Decoder cross-attention test hook: R single-token rows, row r attends over the n_keys keys of audio slot
 // r % n_slots.  q fp32 [R][64*n_head]; k, v fp32 [n_slots][n_head][1536][64] (head-major panels, rounded to
 // bf16 on the device); out fp32 [R][64*n_head].  streaming: 2 tcgen05 kernel, 1 SIMT cp.async.bulk kernel, 0 block-per-head SIMT kernel.

@@ -106,10 +106,27 @@ def test_batch_of_windows_bf16(env):
 
 
 def test_beam_search_bf16(env):
+    """Beam search (5 beams, KV copies between beams, the beams of a window share its cross-KV panels through row groups) with a
+    vocabulary prompt in bf16: well-formed segments whose text is exactly the detokenised tokens, reproducible bit for bit.
+    Token-level parity of this configuration is in test_gpu_headline_parity.py (oracle re-scoring in bf16, token-exact in fp32)."""
     ctx, orc = env.get("base", "fanin", 1)
-    st = ctx.create_state()
-    p = ref_params(env.nw, beam=5)
-    p.set_initial_prompt("Claude Code, Anthropic, Supabase, Vercel")
-    st.full(p, env.synth.synth_clip(2, 30.0))
-    assert st.full_n_segments() >= 0
-    st.close()
+    pcm = env.synth.synth_clip(2, 30.0)
+
+    def run():
+        st = ctx.create_state()
+        p = ref_params(env.nw, beam=5)
+        p.set_initial_prompt("Claude Code, Anthropic, Supabase, Vercel")
+        assert st.full(p, pcm) == 0
+        segs = st.segments()
+        assert st.full_n_segments() == len(segs)
+        st.close()
+        return segs
+
+    a = run()
+    assert a == run()
+    last = None
+    for s in a:
+        assert s["t0"] <= s["t1"] and (last is None or s["t0"] >= last)
+        last = s["t0"]
+        assert all(0 <= t < ctx.n_vocab() for t in s["tokens"])
+        assert s["text"] == b"".join(ctx.token_to_bytes(t) for t in s["tokens"] if t < ctx.token_eot())

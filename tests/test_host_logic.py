@@ -152,3 +152,38 @@ def test_synthetic_model_writer_roundtrip(model_dir):
     assert fb.shape == (80, 201) and np.all(fb >= 0) and np.all(fb.sum(axis=1) > 0)
     assert len(set(ggml_synth.synthetic_vocab())) == 50257
     a.close(); b.close()
+
+
+def test_cross_attention_row_groups(nw):
+    """Host side of the decoder cross-attention's row groups (cross_attention_sm100.cu cross_attention_groups): consecutive rows of one
+    audio slot are one work item of at most 4 rows; the kernel build (group width 1 / 2 / 4) follows the longest run."""
+    import ctypes as C
+    from nobs_whisper_b200 import _lib
+    L = _lib.lib()
+
+    def groups(slots):
+        a = (C.c_int * len(slots))(*slots)
+        g = (C.c_int * (len(slots) + 1))()
+        width = L.whisper_b200_debug_cross_groups(a, len(slots), g)
+        n = g[len(slots)]
+        return width, [(g[i] & 0xFFFFFF, g[i] >> 24) for i in range(n)]
+
+    # a plain step round: every row its own audio -> no groups needed
+    assert groups([5, 6, 7, 9]) == (1, [(0, 1), (1, 1), (2, 1), (3, 1)])
+    # a speculative round: (pass 0, shadow) pairs, one audio without a shadow
+    assert groups([3, 3, 4, 4, 8, 9, 9]) == (2, [(0, 2), (2, 2), (4, 1), (5, 2)])
+    # beam search: five beams per audio -> 4 + 1; the same slot coming back later is a new run
+    assert groups([1] * 5 + [2] * 5 + [1]) == (4, [(0, 4), (4, 1), (5, 4), (9, 1), (10, 1)])
+    # a three-row run needs the 4-wide build; a 9-row prompt is cut 4 + 4 + 1
+    assert groups([7, 7, 7, 2]) == (4, [(0, 3), (3, 1)])
+    assert groups([0] * 9) == (4, [(0, 4), (4, 4), (8, 1)])
+    # every row is covered exactly once, in order
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        slots = np.repeat(rng.integers(0, 6, 20), rng.integers(1, 7, 20)).tolist()
+        width, gs = groups(slots)
+        covered = [r for first, size in gs for r in range(first, first + size)]
+        assert covered == list(range(len(slots)))
+        assert all(1 <= size <= 4 and len(set(slots[first:first + size])) == 1 for first, size in gs)
+        assert width == (1 if max(s for _, s in gs) == 1 else 2 if max(s for _, s in gs) == 2 else 4)
+    assert L.whisper_b200_debug_cross_groups(None, 0, None) == -1
