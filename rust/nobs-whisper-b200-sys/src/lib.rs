@@ -183,6 +183,31 @@ extern "C" {
     pub fn nobs_audio_buffer_take(b: *mut nobs_audio_buffer, n: *mut size_t) -> *const c_float;
     pub fn nobs_audio_buffer_len(b: *const nobs_audio_buffer) -> size_t;
     pub fn nobs_audio_buffer_noise_floor(b: *const nobs_audio_buffer) -> c_float;
+
+    // ---- host-side engine mirror (include/whisper_b200.h: the reference's WhisperEngine, whisper.rs:16-197, above the C ABI)
+    pub fn nobs_engine_new() -> *mut nobs_engine;
+    pub fn nobs_engine_free(e: *mut nobs_engine);
+    pub fn nobs_engine_load_model(e: *mut nobs_engine, path: *const c_char) -> c_int;
+    pub fn nobs_engine_unload_model(e: *mut nobs_engine);
+    pub fn nobs_engine_is_loaded(e: *mut nobs_engine) -> c_int;
+    pub fn nobs_engine_transcribe(e: *mut nobs_engine, audio: *const c_float, n: c_int, language: *const c_char, vocabulary: *const c_char,
+                                  context: *const c_char, out: *mut *const c_char) -> c_int;
+    pub fn nobs_engine_transcribe_chunked(e: *mut nobs_engine, chunks: *const *const c_float, n: *const c_int, n_chunks: c_int, language: *const c_char,
+                                          vocabulary: *const c_char, out: *mut *const c_char) -> c_int;
+    pub fn nobs_engine_transcribe_chunked_parallel(e: *mut nobs_engine, chunks: *const *const c_float, n: *const c_int, n_chunks: c_int,
+                                                   language: *const c_char, vocabulary: *const c_char, abort_on_error: c_int, out: *mut *const c_char,
+                                                   n_decodes: *mut c_int, n_rounds: *mut c_int) -> c_int;
+    pub fn nobs_engine_transcribe_recording(e: *mut nobs_engine, audio: *const c_float, n: size_t, language: *const c_char, vocabulary: *const c_char,
+                                            parallel: c_int, out: *mut *const c_char) -> c_int;
+    pub fn nobs_engine_transcribe_batch(e: *mut nobs_engine, audios: *const *const c_float, n: *const c_int, n_audios: c_int, language: *const c_char,
+                                        vocabulary: *const c_char, beam_size: c_int, texts: *mut *const c_char) -> c_int;
+    pub fn nobs_engine_last_error(e: *mut nobs_engine) -> *const c_char;
+    pub fn nobs_filter_hallucinations(text: *const c_char) -> *const c_char;
+}
+
+#[repr(C)]
+pub struct nobs_engine {
+    _private: [u8; 0],
 }
 
 #[repr(C)]

@@ -183,6 +183,150 @@ pub fn full_batch(ctx: &WhisperContext, states: &mut [WhisperState], params: Ful
     if r != 0 { Err(WhisperError::GenericError(r)) } else { Ok(rc) }
 }
 
+/// The reference's `WhisperEngine` (`src-tauri/src/whisper.rs:16-197`) as one object of the library: same method names, argument meaning
+/// and errors, so `state.rs` can hold this type instead of the reference's struct.  `transcribe_chunked_parallel` and
+/// `transcribe_recording` are the data-parallel forms of `whisper.rs:152-197` / `state.rs:757-792`: same text as the sequential loop
+/// (chunk k's prompt is the text of the last non-empty chunk before it), decoded in speculative batches on the GPU.
+pub mod engine {
+    use super::sys;
+    use std::ffi::{CStr, CString};
+    use std::fmt;
+    use std::os::raw::{c_char, c_int};
+    use std::ptr;
+
+    /// whisper.rs:7-14
+    #[derive(Debug)]
+    pub enum WhisperError {
+        LoadError(String),
+        TranscriptionError(String),
+        NoModel,
+    }
+    impl fmt::Display for WhisperError {
+        fn fmt(&self, f: &mut fmt::Formatter<'_>) -> fmt::Result {
+            match self {
+                WhisperError::LoadError(m) => write!(f, "Failed to load model: {}", m),
+                WhisperError::TranscriptionError(m) => write!(f, "Transcription failed: {}", m),
+                WhisperError::NoModel => write!(f, "No model loaded"),
+            }
+        }
+    }
+    impl std::error::Error for WhisperError {}
+
+    /// Speculation bookkeeping of `transcribe_chunked_parallel`: `decodes == chunks` means no chunk was decoded twice.
+    #[derive(Debug, Clone, Copy, Default)]
+    pub struct ChainStats {
+        pub decodes: i32,
+        pub rounds: i32,
+    }
+
+    pub struct WhisperEngine(*mut sys::nobs_engine);
+    unsafe impl Send for WhisperEngine {}
+
+    fn opt_cstring(s: Option<&str>) -> Result<Option<CString>, WhisperError> {
+        match s {
+            None => Ok(None),
+            Some(v) => CString::new(v).map(Some).map_err(|_| WhisperError::TranscriptionError("NUL byte in string".into())),
+        }
+    }
+    fn ptr_or_null(s: &Option<CString>) -> *const c_char {
+        s.as_ref().map_or(ptr::null(), |c| c.as_ptr())
+    }
+
+    impl WhisperEngine {
+        /// whisper.rs:22-27
+        pub fn new() -> Self {
+            WhisperEngine(unsafe { sys::nobs_engine_new() })
+        }
+        fn last_error(&self) -> String {
+            let p = unsafe { sys::nobs_engine_last_error(self.0) };
+            if p.is_null() { String::new() } else { unsafe { CStr::from_ptr(p) }.to_string_lossy().into_owned() }
+        }
+        fn finish(&self, rc: c_int, out: *const c_char) -> Result<String, WhisperError> {
+            match rc {
+                0 if !out.is_null() => Ok(unsafe { CStr::from_ptr(out) }.to_string_lossy().into_owned()),
+                3 => Err(WhisperError::NoModel),
+                _ => Err(WhisperError::TranscriptionError(self.last_error())),
+            }
+        }
+        /// whisper.rs:36-52
+        pub fn load_model(&mut self, path: &str) -> Result<(), WhisperError> {
+            let c = CString::new(path).map_err(|_| WhisperError::LoadError("NUL byte in path".into()))?;
+            if unsafe { sys::nobs_engine_load_model(self.0, c.as_ptr()) } == 0 { Ok(()) } else { Err(WhisperError::LoadError(self.last_error())) }
+        }
+        /// whisper.rs:55-59
+        pub fn unload_model(&mut self) {
+            unsafe { sys::nobs_engine_unload_model(self.0) }
+        }
+        /// whisper.rs:62-64
+        pub fn is_loaded(&self) -> bool {
+            unsafe { sys::nobs_engine_is_loaded(self.0) != 0 }
+        }
+        /// whisper.rs:66-148
+        pub fn transcribe(&self, audio: &[f32], language: Option<&str>, vocabulary: Option<&str>, context: Option<&str>) -> Result<String, WhisperError> {
+            let (l, v, c) = (opt_cstring(language)?, opt_cstring(vocabulary)?, opt_cstring(context)?);
+            let mut out: *const c_char = ptr::null();
+            let rc = unsafe {
+                sys::nobs_engine_transcribe(self.0, audio.as_ptr(), audio.len() as c_int, ptr_or_null(&l), ptr_or_null(&v), ptr_or_null(&c), &mut out)
+            };
+            self.finish(rc, out)
+        }
+        /// whisper.rs:152-197 (sequential: chunk k is decoded after chunk k - 1)
+        pub fn transcribe_chunked(&self, chunks: &[Vec<f32>], language: Option<&str>, vocabulary: Option<&str>) -> Result<String, WhisperError> {
+            let (l, v) = (opt_cstring(language)?, opt_cstring(vocabulary)?);
+            let ptrs: Vec<*const f32> = chunks.iter().map(|c| c.as_ptr()).collect();
+            let ns: Vec<c_int> = chunks.iter().map(|c| c.len() as c_int).collect();
+            let mut out: *const c_char = ptr::null();
+            let rc = unsafe {
+                sys::nobs_engine_transcribe_chunked(self.0, ptrs.as_ptr(), ns.as_ptr(), ptrs.len() as c_int, ptr_or_null(&l), ptr_or_null(&v), &mut out)
+            };
+            self.finish(rc, out)
+        }
+        /// The same result, chunks decoded together in speculative batches.
+        pub fn transcribe_chunked_parallel(&self, chunks: &[Vec<f32>], language: Option<&str>, vocabulary: Option<&str>)
+                                           -> Result<(String, ChainStats), WhisperError> {
+            let (l, v) = (opt_cstring(language)?, opt_cstring(vocabulary)?);
+            let ptrs: Vec<*const f32> = chunks.iter().map(|c| c.as_ptr()).collect();
+            let ns: Vec<c_int> = chunks.iter().map(|c| c.len() as c_int).collect();
+            let mut out: *const c_char = ptr::null();
+            let mut stats = ChainStats::default();
+            let rc = unsafe {
+                sys::nobs_engine_transcribe_chunked_parallel(self.0, ptrs.as_ptr(), ns.as_ptr(), ptrs.len() as c_int, ptr_or_null(&l), ptr_or_null(&v),
+                                                             1, &mut out, &mut stats.decodes, &mut stats.rounds)
+            };
+            self.finish(rc, out).map(|t| (t, stats))
+        }
+        /// state.rs:757-792: what is left of a recording when it stops (16 kHz mono).  parallel: 0 = pieces in order with the previous
+        /// text as context, 1 = pieces decoded independently, 2 = chained AND data-parallel (same text as 0).
+        pub fn transcribe_recording(&self, audio: &[f32], language: Option<&str>, vocabulary: Option<&str>, parallel: i32) -> Result<String, WhisperError> {
+            let (l, v) = (opt_cstring(language)?, opt_cstring(vocabulary)?);
+            let mut out: *const c_char = ptr::null();
+            let rc = unsafe {
+                sys::nobs_engine_transcribe_recording(self.0, audio.as_ptr(), audio.len(), ptr_or_null(&l), ptr_or_null(&v), parallel as c_int, &mut out)
+            };
+            self.finish(rc, out)
+        }
+    }
+    impl Default for WhisperEngine {
+        fn default() -> Self { Self::new() }
+    }
+    impl Drop for WhisperEngine {
+        fn drop(&mut self) {
+            unsafe { sys::nobs_engine_free(self.0) }
+        }
+    }
+
+    /// whisper.rs:233-260
+    pub fn filter_hallucinations(text: &str) -> String {
+        match CString::new(text) {
+            Err(_) => text.to_string(),
+            Ok(c) => {
+                let p = unsafe { sys::nobs_filter_hallucinations(c.as_ptr()) };
+                if p.is_null() { String::new() } else { unsafe { CStr::from_ptr(p) }.to_string_lossy().into_owned() }
+            }
+        }
+    }
+}
+
 /// Drop-in bodies for the reference's `src-tauri/src/audio.rs` functions (same names and signatures), backed by the
 /// library: the window-RMS scan and the resampler run on the GPU, the capture buffer is host logic in the library.
 pub mod audio {
