@@ -187,3 +187,39 @@ def test_cross_attention_row_groups(nw):
         assert all(1 <= size <= 4 and len(set(slots[first:first + size])) == 1 for first, size in gs)
         assert width == (1 if max(s for _, s in gs) == 1 else 2 if max(s for _, s in gs) == 2 else 4)
     assert L.whisper_b200_debug_cross_groups(None, 0, None) == -1
+
+
+def test_rust_sys_crate_matches_the_header(nw):
+    """rustc is not in this image, so the FFI stub a maintainer links (rust/nobs-whisper-b200-sys) is held to the C ABI textually:
+    every function its extern block declares is exported by the library, declared in include/whisper_b200.h, and takes the same
+    number of arguments there."""
+    from nobs_whisper_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rust = open(os.path.join(root, "rust", "nobs-whisper-b200-sys", "src", "lib.rs")).read()
+    header = open(os.path.join(root, "include", "whisper_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+
+    def n_args(arglist):
+        arglist = arglist.strip()
+        if arglist in ("", "void"):
+            return 0
+        depth, n = 0, 1
+        for ch in arglist:
+            depth += ch in "(<["
+            depth -= ch in ")>]"
+            n += ch == "," and depth == 0
+        return n
+
+    c_decl = {m.group(1): n_args(m.group(2)) for m in re.finditer(r"\b((?:whisper|nobs)_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)}
+    externs = "".join(re.findall(r'extern "C" \{(.*?)\n\}', rust, flags=re.S))
+    rust_decl = {m.group(1): n_args(m.group(2)) for m in re.finditer(r"pub fn (\w+)\(([^;]*?)\)\s*(?:->[^;]*)?;", externs, flags=re.S)}
+    assert len(rust_decl) >= 45
+    raw = _lib.lib()
+    for name, n in sorted(rust_decl.items()):
+        assert hasattr(raw, name), name
+        assert name in c_decl, name
+        assert c_decl[name] == n, (name, c_decl[name], n)
+    # the wrapper crate only calls what the sys crate declares
+    wrapper = open(os.path.join(root, "rust", "nobs-whisper-b200", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::((?:whisper|nobs)_[a-z0-9_]+)\s*\(", wrapper))
+    assert used and used <= set(rust_decl), sorted(used - set(rust_decl))
