@@ -194,6 +194,62 @@ def beam5_latency(n_clips: int):
             "segments": int(rows), "timing": "host wall clock around WhisperState.full + segment read-back (H2D of the PCM and D2H of the text included)"}
 
 
+def single_pass_child(args):
+    """Child process of the default run (`--single-pass-child`): the SAME clips and model with `temperature_inc = 0`, i.e. one decoding
+    pass per window — what the workload costs when the first pass is accepted, as trained weights do on clean speech.  NOT the
+    reference's parameters (it inherits the 0.2 ladder; on random-init weights every window then runs all six passes): an auxiliary
+    figure next to the headline, printed as one JSON object."""
+    import nobs_whisper_b200 as nw
+    path = ensure_model(args.model, 0, 1, lambda: None)
+    ctx = nw.WhisperContext.new_with_params(path, nw.WhisperContextParameters.default(), precision=args.precision)
+    audio = make_audio(args.windows, 0)
+
+    def params():
+        p = nw.FullParams.new(nw.SamplingStrategy.Greedy(best_of=1))
+        p.set_language("en")
+        p.set_no_context(False); p.set_suppress_blank(True); p.set_no_speech_thold(0.6); p.set_entropy_thold(2.4); p.set_logprob_thold(-1.0)
+        p.set_temperature_inc(0.0)
+        return p
+
+    secs, windows, segments = [], 0, 0
+    for i in range(1 + args.single_pass_steps):   # one warm-up step
+        states = [ctx.create_state() for _ in audio]
+        t0 = time.perf_counter()
+        rc = nw.full_batch(ctx, states, params(), audio)
+        n_seg = sum(st.full_n_segments() for st in states)
+        dt = time.perf_counter() - t0
+        if any(rc):
+            raise RuntimeError(f"full_batch rc {rc}")
+        if i >= 1:
+            secs.append(dt)
+            windows += sum(int(st.stats().n_windows) for st in states)
+            segments += n_seg
+        for st in states:
+            st.close()
+    ctx.close()
+    n = len(secs)
+    print(json.dumps({"value": args.windows * WINDOW_S * n / sum(secs), "unit": "audio-s/s", "ms_per_step": 1e3 * sum(secs) / n, "steps": n,
+                      "windows_encoded_per_step": windows / n, "segments_per_step": segments / n,
+                      "workload": f"whisper {args.model} {args.precision}, the same {args.windows} x 30-s clips, greedy best_of=1 with temperature_inc = 0: ONE decoding pass "
+                                  "per window (the cost of the workload when the first pass is accepted); not the reference's parameters — auxiliary figure",
+                      "timing": "host wall clock around whisper_b200_full_batch + segment counts, pageable host PCM (H2D inside)"}), flush=True)
+
+
+def single_pass_figure(args):
+    """Runs single_pass_child in its own process (its own context; a failure there cannot take the headline line with it)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--single-pass-child", "--model", args.model, "--windows", str(args.windows),
+           "--precision", args.precision, "--single-pass-steps", str(args.single_pass_steps)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=args.single_pass_timeout_s)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"rc {r.returncode}: " + (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+        return json.loads(lines[-1])
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 def run_reference(args, rank, world, arch_name):
     """--impl reference: the oracle port on the host cores, bounded sample per step."""
     if rank != 0:
@@ -261,6 +317,9 @@ def main():
     ap.add_argument("--no-cpu-4threads", action="store_true", help="skip the second cpu_baseline pass at the upstream default of 4 threads")
     ap.add_argument("--latency-clips", type=int, default=200, help="5-s utterances for the large-v3-turbo latency figure (0: skip); BASELINE config 5 asks for >= 200")
     ap.add_argument("--beam-clips", type=int, default=20, help="30-s windows for the base / beam 5 / vocabulary-prompt latency figure of BASELINE config 2 (0: skip)")
+    ap.add_argument("--single-pass-steps", type=int, default=2, help="timed steps of the auxiliary one-pass-per-window figure (temperature_inc = 0; 0: skip)")
+    ap.add_argument("--single-pass-timeout-s", type=float, default=240.0)
+    ap.add_argument("--single-pass-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU transcribes its own --windows windows; strong: --windows windows in total (BASELINE config 4: one hour = 120 windows), "
                          "rank r takes shard_range(windows, world, r)")
@@ -270,6 +329,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.single_pass_child:
+        single_pass_child(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world, args.model)
         return
@@ -458,6 +520,9 @@ def main():
                 latency_beam5 = beam5_latency(args.beam_clips)
             except Exception as exc:  # auxiliary figure: never lose the headline line to it
                 latency_beam5 = {"error": str(exc)}
+        single_pass = None
+        if args.single_pass_steps > 0 and world == 1 and not args.no_cpu_baseline:   # part of the default run only
+            single_pass = single_pass_figure(args)
         line = {
             "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt_dev / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -486,6 +551,7 @@ def main():
             "clocks": clocks,
             "latency": latency,
             "latency_beam5": latency_beam5,
+            "single_pass": single_pass,
         }
         print(json.dumps(line, default=float), flush=True)
     eng.close()
